@@ -1,0 +1,909 @@
+// drj_host.cu -- host side of libdrjacoby_b200.so: the C ABI of include/drjacoby_b200.h.
+//
+// Replaces (reference): the .Call entry _drjacoby_main_cpp (src/RcppExports.cpp:15-24), System::load
+// (src/System.cpp:7-45), and the driver part of run_mcmc<T1,T2> (src/main.cpp:84-278): allocation of
+// the output stores (:118-124), the burn-in / sampling loops (:153-251), the accept-count reset
+// between phases (:208-210), and the returned list (:268-276) -- for ALL chains of a run at once.
+// The per-particle work (Particle::update, coupling) is in drj_sampler.cuh.
+//
+// There is deliberately no CPU fallback: every compute entry point fails with DRJ_ERR_CUDA when no
+// device is present.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/drjacoby_b200.h"
+#include "drj_models.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+static int set_err(drj_error* e, int code, const char* fmt, ...) {
+  if (e) {
+    e->code = code;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(e->message, sizeof(e->message), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CUDA_TRY(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return set_err(err, DRJ_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), \
+                     __FILE__, __LINE__, cudaGetErrorString(_e));                            \
+  } while (0)
+
+static double wall_now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+// auxiliary kernels
+// ------------------------------------------------------------------------------------------------
+// dst[n * dst_stride + dst_off + c] = src[c * N + n]   (ring [c][n]  ->  per-series [n][c])
+__global__ void drj_transpose_rows(const double* __restrict__ src, long long N, int ncols, double* __restrict__ dst,
+                                   long long dst_stride, long long dst_off) {
+  __shared__ double tile[32][33];
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long n = n0 + threadIdx.x;
+    if (c < ncols && n < N) tile[j][threadIdx.x] = src[(long long)c * N + n];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long n = n0 + j;
+    const int c = c0 + threadIdx.x;
+    if (c < ncols && n < N) dst[n * dst_stride + dst_off + c] = tile[threadIdx.x][j];
+  }
+}
+
+// bw_final[p][i] = exp(logbw[i][p])
+__global__ void drj_export_bw(const double* __restrict__ logbw, long long P, int D, double* __restrict__ out) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  for (int i = 0; i < D; ++i) out[p * D + i] = exp(logbw[(long long)i * P + p]);
+}
+
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread
+__global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// models: built-in registry + NVRTC
+// ------------------------------------------------------------------------------------------------
+struct drj_model {
+  std::string name;
+  int D = 0, NBLOCK = 0;
+  bool datum_form = false;
+  bool jit = false;
+  const void* init_fn = nullptr;   // built-in: __global__ function addresses
+  const void* sweep_fn = nullptr;
+  CUmodule module = nullptr;       // jit
+  CUfunction init_cu = nullptr, sweep_cu = nullptr;
+  double compile_seconds = 0.0;
+  int device = 0;
+};
+
+struct BuiltinEntry {
+  const char* name;
+  int D, NBLOCK;
+  bool datum_form;
+  const void* init_fn;
+  const void* sweep_fn;
+};
+
+#define DRJ_REG(NAME, ...)                                                               \
+  {                                                                                      \
+    NAME, __VA_ARGS__::D, __VA_ARGS__::NBLOCK, __VA_ARGS__::DATUM_FORM,                  \
+        (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__> \
+  }
+
+static const BuiltinEntry BUILTINS[] = {
+    DRJ_REG("example", DrjModelExample),
+    DRJ_REG("example_exact", DrjModelExampleExact),
+    DRJ_REG("coupling", DrjModelCoupling),
+    DRJ_REG("normal_mu", DrjModelNormalMu),
+    DRJ_REG("doublewell", DrjModelDoubleWell),
+    DRJ_REG("multilevel", DrjModelMultilevel<5>),
+    DRJ_REG("multilevel", DrjModelMultilevel<50>),
+    DRJ_REG("blocks", DrjModelBlocks<6>),
+    DRJ_REG("returnprior", DrjModelReturnPrior),
+    DRJ_REG("testfile", DrjModelTestFile<true, true>),
+    DRJ_REG("testfile_nullprior", DrjModelTestFile<true, false>),
+    DRJ_REG("testfile_nulllike", DrjModelTestFile<false, true>),
+    DRJ_REG("logistic", DrjModelLogistic),
+    DRJ_REG("const", DrjModelConst),
+    DRJ_REG("halfdomain_like", DrjModelHalfDomain<true>),
+    DRJ_REG("halfdomain_prior", DrjModelHalfDomain<false>),
+};
+static const int N_BUILTINS = (int)(sizeof(BUILTINS) / sizeof(BUILTINS[0]));
+
+// ---- driver entry points (no link-time dependency on libcuda: the library must load on a CPU box)
+struct DriverApi {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                           CUstream, void**, void**) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+};
+static DriverApi g_drv;
+static std::mutex g_mutex;
+
+static bool load_driver_api() {
+  if (g_drv.ok) return true;
+  struct { const char* sym; void** slot; } want[] = {
+      {"cuModuleLoadData", (void**)&g_drv.ModuleLoadData},
+      {"cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction},
+      {"cuModuleUnload", (void**)&g_drv.ModuleUnload},
+      {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
+      {"cuGetErrorString", (void**)&g_drv.GetErrorString},
+  };
+  for (auto& w : want) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(w.sym, w.slot, cudaEnableDefault, &q) != cudaSuccess || !*w.slot) return false;
+  }
+  g_drv.ok = true;
+  return true;
+}
+
+// ---- NVRTC through dlopen (optional at load time, required only for source models)
+struct NvrtcApi {
+  void* handle = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  const char* (*GetErrorString)(nvrtcResult);
+};
+static NvrtcApi g_nvrtc;
+
+static bool load_nvrtc(std::string& why) {
+  if (g_nvrtc.handle) return true;
+  const char* cands[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                         "/usr/local/cuda/lib64/libnvrtc.so"};
+  void* h = nullptr;
+  for (const char* c : cands) {
+    h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+    if (h) break;
+  }
+  if (!h) { why = "libnvrtc.so.12 not found"; return false; }
+#define NV_SYM(field, name)                              \
+  *(void**)(&g_nvrtc.field) = dlsym(h, name);            \
+  if (!g_nvrtc.field) { why = std::string("missing ") + name; dlclose(h); return false; }
+  NV_SYM(CreateProgram, "nvrtcCreateProgram")
+  NV_SYM(DestroyProgram, "nvrtcDestroyProgram")
+  NV_SYM(CompileProgram, "nvrtcCompileProgram")
+  NV_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+  NV_SYM(GetCUBIN, "nvrtcGetCUBIN")
+  NV_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+  NV_SYM(GetProgramLog, "nvrtcGetProgramLog")
+  NV_SYM(GetErrorString, "nvrtcGetErrorString")
+#undef NV_SYM
+  g_nvrtc.handle = h;
+  return true;
+}
+
+// the device headers, embedded at build time (csrc/build.py writes drj_embedded_sources.inc)
+static const char* const EMBED_DEVICE =
+#include "drj_embedded_device.inc"
+    ;
+static const char* const EMBED_SAMPLER =
+#include "drj_embedded_sampler.inc"
+    ;
+static const char* const EMBED_MODELS =
+#include "drj_embedded_models.inc"
+    ;
+
+static uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ULL;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; }
+  return h;
+}
+
+static bool valid_ident(const char* s) {
+  if (!s || !*s) return false;
+  if (!(isalpha((unsigned char)s[0]) || s[0] == '_')) return false;
+  for (const char* p = s; *p; ++p)
+    if (!(isalnum((unsigned char)*p) || *p == '_')) return false;
+  return true;
+}
+
+static std::string cache_dir() {
+  const char* e = getenv("DRJ_CACHE_DIR");
+  std::string d = e ? e : (std::string("/tmp/drjacoby_b200_cache_") + std::to_string((long)getuid()));
+  mkdir(d.c_str(), 0700);
+  return d;
+}
+
+// Generates the translation unit for a source model: index constants from the name arrays, the
+// user's code, the model struct that adapts it to the sampler contract, and the two kernels.
+static std::string make_jit_source(const drj_model_desc* desc) {
+  std::string s;
+  s += "#include \"drj_models.cuh\"\n";
+  for (int i = 0; i < desc->d; ++i)
+    if (desc->param_names && valid_ident(desc->param_names[i]))
+      s += "constexpr int P_" + std::string(desc->param_names[i]) + " = " + std::to_string(i) + ";\n";
+  for (int i = 0; i < desc->n_data_items; ++i)
+    if (desc->data_names && valid_ident(desc->data_names[i]))
+      s += "constexpr int DATA_" + std::string(desc->data_names[i]) + " = " + std::to_string(i) + ";\n";
+  for (int i = 0; i < desc->n_misc_items; ++i)
+    if (desc->misc_names && valid_ident(desc->misc_names[i]))
+      s += "constexpr int MISC_" + std::string(desc->misc_names[i]) + " = " + std::to_string(i) + ";\n";
+  s += "constexpr int DRJ_D = " + std::to_string(desc->d) + ";\n";
+  s += "constexpr int DRJ_NBLOCK = " + std::to_string(desc->n_block) + ";\n";
+  s += "#line 1 \"user_model.cu\"\n";
+  s += desc->cuda_source;
+  s += "\n#line 1 \"drj_user_glue.cu\"\n";
+  const std::string ll = desc->loglike_name ? desc->loglike_name : "loglike";
+  const std::string lp = desc->logprior_name ? desc->logprior_name : "logprior";
+  s += "#ifndef DRJ_USER_MODEL\n"
+       "struct DrjUserModel {\n"
+       "  static constexpr int D = DRJ_D, NBLOCK = DRJ_NBLOCK;\n"
+       "  static constexpr bool DATUM_FORM = false;\n"
+       "  __device__ static __forceinline__ double loglike(const double* th, const DrjList& data, const DrjList& misc, int block) {\n"
+       "    return ::" + ll + "(th, data, misc, block);\n"
+       "  }\n"
+       "  __device__ static __forceinline__ double logprior(const double* th, const DrjList& misc) {\n"
+       "    return ::" + lp + "(th, misc);\n"
+       "  }\n"
+       "};\n"
+       "#define DRJ_USER_MODEL DrjUserModel\n"
+       "#endif\n"
+       "static_assert(DRJ_USER_MODEL::D == DRJ_D, \"model D does not match df_params\");\n"
+       "static_assert(DRJ_USER_MODEL::NBLOCK == DRJ_NBLOCK, \"model NBLOCK does not match df_params$block\");\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  drj_init_body<DRJ_USER_MODEL>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  drj_sweep_body<DRJ_USER_MODEL>(a);\n"
+       "}\n";
+  return s;
+}
+
+static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
+  const double t0 = wall_now();
+  const std::string src = make_jit_source(desc);
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v1";
+  char hex[32];
+  snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)fnv1a(key_text));
+  const std::string path = cache_dir() + "/" + hex + ".cubin";
+  std::vector<char> cubin;
+  if (FILE* f = fopen(path.c_str(), "rb")) {
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n > 0) {
+      cubin.resize(n);
+      if (fread(cubin.data(), 1, n, f) != (size_t)n) cubin.clear();
+    }
+    fclose(f);
+  }
+  if (cubin.empty()) {
+    std::string why;
+    if (!load_nvrtc(why)) return set_err(err, DRJ_ERR_COMPILE, "NVRTC unavailable: %s", why.c_str());
+    nvrtcProgram prog;
+    const char* hdr_src[] = {EMBED_DEVICE, EMBED_SAMPLER, EMBED_MODELS};
+    const char* hdr_name[] = {"drj_device.cuh", "drj_sampler.cuh", "drj_models.cuh"};
+    nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "drj_jit_model.cu", 3, hdr_src, hdr_name);
+    if (r != NVRTC_SUCCESS) return set_err(err, DRJ_ERR_COMPILE, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+    r = g_nvrtc.CompileProgram(prog, 4, opts);
+    if (r != NVRTC_SUCCESS) {
+      size_t n = 0;
+      g_nvrtc.GetProgramLogSize(prog, &n);
+      std::string log(n, '\0');
+      if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+      g_nvrtc.DestroyProgram(&prog);
+      return set_err(err, DRJ_ERR_COMPILE, "NVRTC compile failed: %.440s", log.c_str());
+    }
+    size_t n = 0;
+    g_nvrtc.GetCUBINSize(prog, &n);
+    cubin.resize(n);
+    g_nvrtc.GetCUBIN(prog, cubin.data());
+    g_nvrtc.DestroyProgram(&prog);
+    m->compile_seconds = wall_now() - t0;
+    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      fwrite(cubin.data(), 1, cubin.size(), f);
+      fclose(f);
+      rename(tmp.c_str(), path.c_str());
+    }
+  }
+  if (!load_driver_api()) return set_err(err, DRJ_ERR_CUDA, "CUDA driver entry points unavailable");
+  CUresult cr = g_drv.ModuleLoadData(&m->module, cubin.data());
+  if (cr != CUDA_SUCCESS) {
+    const char* es = nullptr;
+    g_drv.GetErrorString(cr, &es);
+    return set_err(err, DRJ_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
+  }
+  if (g_drv.ModuleGetFunction(&m->init_cu, m->module, "drj_user_init") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&m->sweep_cu, m->module, "drj_user_sweep") != CUDA_SUCCESS)
+    return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
+  return DRJ_OK;
+}
+
+extern "C" int drj_abi_version(void) { return DRJ_ABI_VERSION; }
+
+extern "C" int drj_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int drj_builtin_model_count(void) { return N_BUILTINS; }
+extern "C" const char* drj_builtin_model_name(int i) { return (i >= 0 && i < N_BUILTINS) ? BUILTINS[i].name : nullptr; }
+
+extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_model** out, drj_error* err) {
+  if (!desc || !out) return set_err(err, DRJ_ERR_ARG, "drj_model_create: NULL argument");
+  *out = nullptr;
+  if (desc->builtin) {
+    for (int i = 0; i < N_BUILTINS; ++i) {
+      const BuiltinEntry& b = BUILTINS[i];
+      if (strcmp(b.name, desc->builtin) != 0) continue;
+      if (desc->d > 0 && (b.D != desc->d || (desc->n_block > 0 && b.NBLOCK != desc->n_block))) continue;
+      drj_model* m = new drj_model();
+      m->name = b.name; m->D = b.D; m->NBLOCK = b.NBLOCK; m->datum_form = b.datum_form;
+      m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->device = device;
+      *out = m;
+      return DRJ_OK;
+    }
+    // a sized family (multilevel<G>, blocks<G>) not pre-instantiated: specialise it with NVRTC
+    std::string fam = desc->builtin;
+    std::string glue;
+    if (fam == "multilevel" && desc->d > 0)
+      glue = "#define DRJ_USER_MODEL DrjModelMultilevel<" + std::to_string(desc->d) + ">\n";
+    else if (fam == "blocks" && desc->d > 3)
+      glue = "#define DRJ_USER_MODEL DrjModelBlocks<" + std::to_string(desc->d - 3) + ">\n";
+    else
+      return set_err(err, DRJ_ERR_MODEL, "unknown built-in model '%s' (d=%d, n_block=%d)", desc->builtin, desc->d, desc->n_block);
+    drj_model_desc jd = *desc;
+    jd.builtin = nullptr;
+    jd.cuda_source = glue.c_str();
+    jd.param_names = nullptr; jd.data_names = nullptr; jd.misc_names = nullptr;
+    jd.n_block = desc->d + 1 - (fam == "blocks" ? 3 : 0);
+    return drj_model_create(&jd, device, out, err);
+  }
+  if (!desc->cuda_source) return set_err(err, DRJ_ERR_MODEL, "model has neither a built-in name nor CUDA source");
+  if (desc->d < 1 || desc->n_block < 1) return set_err(err, DRJ_ERR_ARG, "source model needs d >= 1 and n_block >= 1");
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return set_err(err, DRJ_ERR_CUDA, "no CUDA device %d", device); }
+  cudaFree(0);  // make sure the primary context exists before the driver API is used
+  std::lock_guard<std::mutex> lock(g_mutex);
+  drj_model* m = new drj_model();
+  m->name = "jit"; m->D = desc->d; m->NBLOCK = desc->n_block; m->jit = true; m->device = device;
+  int rc = jit_compile(desc, m, err);
+  if (rc != DRJ_OK) { delete m; return rc; }
+  *out = m;
+  return DRJ_OK;
+}
+
+extern "C" void drj_model_destroy(drj_model* m) {
+  if (!m) return;
+  if (m->module && g_drv.ok) g_drv.ModuleUnload(m->module);
+  delete m;
+}
+
+extern "C" double drj_model_compile_seconds(const drj_model* m) { return m ? m->compile_seconds : 0.0; }
+
+// ------------------------------------------------------------------------------------------------
+// session
+// ------------------------------------------------------------------------------------------------
+struct drj_session {
+  drj_config cfg;
+  const drj_model* model = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DrjKernelArgs a;
+  std::vector<void*> allocs;
+  int D = 0, B = 0, R = 0, C = 0;
+  long long P = 0, Ppt = 0, Pth = 0;
+  int d_free = 0;
+  int tb = 1;        // iterations per launch (ring depth)
+  int cpc = 1, nthreads = 32, grid = 1;
+  int t_done = 0;    // updates done (0 .. burnin-1+samples)
+  int T_total = 0;
+  // device outputs
+  double *fin_ll_b = nullptr, *fin_lp_b = nullptr, *fin_th_b = nullptr;
+  double *fin_ll_s = nullptr, *fin_lp_s = nullptr, *fin_th_s = nullptr;
+  int *mc_b = nullptr, *mc_s = nullptr, *acc_b = nullptr;
+  unsigned long long* err_key = nullptr;
+  int64_t sweep_launches = 0, aux_launches = 0;
+  double t_create = 0.0;
+  bool failed = false;
+};
+
+template <class T>
+static cudaError_t dalloc(drj_session* s, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e == cudaSuccess) { s->allocs.push_back(q); *p = (T*)q; }
+  return e;
+}
+
+template <class T>
+static cudaError_t upload(drj_session* s, const T** dev, const T* host, size_t n) {
+  T* q = nullptr;
+  cudaError_t e = dalloc(s, &q, n);
+  if (e != cudaSuccess) return e;
+  *dev = q;
+  if (n) e = cudaMemcpyAsync(q, host, n * sizeof(T), cudaMemcpyHostToDevice, s->stream);
+  return e;
+}
+
+// data / misc list -> device, every item 16-byte aligned and the buffer padded by one tile so the
+// TMA engine can always fetch whole tiles
+static cudaError_t upload_list(drj_session* s, const drj_list* l, DrjList* out) {
+  const int n = l ? l->n_items : 0;
+  std::vector<long long> off(std::max(n, 1), 0), len(std::max(n, 1), 0);
+  long long total = 0;
+  for (int k = 0; k < n; ++k) {
+    off[k] = total;
+    len[k] = l->lengths[k];
+    total += (len[k] + 1) & ~1LL;
+  }
+  double* vals = nullptr;
+  cudaError_t e = dalloc(s, &vals, (size_t)total + DRJ_TILE + 2);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(vals, 0, ((size_t)total + DRJ_TILE + 2) * sizeof(double), s->stream);
+  if (e != cudaSuccess) return e;
+  for (int k = 0; k < n; ++k)
+    if (len[k] > 0) {
+      e = cudaMemcpyAsync(vals + off[k], l->values + l->offsets[k], (size_t)len[k] * sizeof(double),
+                          cudaMemcpyHostToDevice, s->stream);
+      if (e != cudaSuccess) return e;
+    }
+  const long long *doff = nullptr, *dlen = nullptr;
+  e = upload(s, &doff, off.data(), off.size());
+  if (e != cudaSuccess) return e;
+  e = upload(s, &dlen, len.data(), len.size());
+  if (e != cudaSuccess) return e;
+  // the host vectors must outlive the async copies
+  e = cudaStreamSynchronize(s->stream);
+  out->values = vals; out->offsets = doff; out->lengths = dlen; out->n_items = n;
+  return e;
+}
+
+static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
+  const drj_model* m = s->model;
+  void* params[] = {(void*)&s->a};
+  if (m->jit) {
+    CUresult cr = g_drv.LaunchKernel(sweep ? m->sweep_cu : m->init_cu, s->grid, 1, 1, s->nthreads, 1, 1, 0,
+                                     (CUstream)s->stream, params, nullptr);
+    if (cr != CUDA_SUCCESS) {
+      const char* es = nullptr;
+      g_drv.GetErrorString(cr, &es);
+      return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernel: %s", es ? es : "?");
+    }
+  } else {
+    CUDA_TRY(cudaLaunchKernel(sweep ? m->sweep_fn : m->init_fn, dim3(s->grid), dim3(s->nthreads), params, 0, s->stream));
+  }
+  return DRJ_OK;
+}
+
+static int transpose_to(drj_session* s, const double* ring, long long N, int ncols, double* dst, long long dst_stride,
+                        long long dst_off, drj_error* err) {
+  if (ncols <= 0 || N <= 0) return DRJ_OK;
+  dim3 block(32, 8);
+  for (int c0 = 0; c0 < ncols; c0 += 32 * 65535) {
+    const int nc = std::min(ncols - c0, 32 * 65535);
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((nc + 31) / 32));
+    drj_transpose_rows<<<grid, block, 0, s->stream>>>(ring + (long long)c0 * N, N, nc, dst, dst_stride, dst_off + c0);
+    s->aux_launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DRJ_OK;
+}
+
+// move `nt` ring rows into the final per-series layout at column `col0` of phase `sampling`
+static int flush_ring(drj_session* s, int nt, bool sampling, int col0, drj_error* err) {
+  const int L = sampling ? s->cfg.samples : s->cfg.burnin;
+  int rc;
+  if ((rc = transpose_to(s, s->a.ring_ll, s->Ppt, nt, sampling ? s->fin_ll_s : s->fin_ll_b, L, col0, err))) return rc;
+  if ((rc = transpose_to(s, s->a.ring_lp, s->Ppt, nt, sampling ? s->fin_lp_s : s->fin_lp_b, L, col0, err))) return rc;
+  // theta ring [nt][D][Pth] is [nt*D][Pth]: column (t*D + i) -> dst[(n*L + col0 + t)*D + i]
+  return transpose_to(s, s->a.ring_theta, s->Pth, nt * s->D, sampling ? s->fin_th_s : s->fin_th_b,
+                      (long long)L * s->D, (long long)col0 * s->D, err);
+}
+
+static const char* code_message(int code) {
+  switch (code) {
+    case DRJ_ERR_INIT_NEGINF:
+      return "Starting values result in -Inf in likelihood or prior. Consider setting inital values in the parameters data.frame.";
+    case DRJ_ERR_LOGLIKE_BAD: return "NA, NaN or Inf in likelihood";
+    case DRJ_ERR_LOGPRIOR_BAD: return "NA, NaN or Inf in prior";
+    case DRJ_ERR_TRANS_TYPE: return "trans_type invalid";
+    default: return "error";
+  }
+}
+
+// after a synchronised launch: did any particle report an error?  (launch_iter0 = global update index of
+// the launch's first iteration, 0 for init)
+static int check_device_error(drj_session* s, int launch_iter0, drj_error* err) {
+  unsigned long long key = 0;
+  CUDA_TRY(cudaMemcpy(&key, s->err_key, sizeof(key), cudaMemcpyDeviceToHost));
+  if (key == ~0ULL) return DRJ_OK;
+  const int it = (int)(key >> 44);
+  const long long chain = (long long)((key >> 20) & 0xFFFFFF);
+  const int rung = (int)((key >> 10) & 0x3FF);
+  const int param = (int)(key & 0x3FF) - 1;
+  const long long p = chain * s->R + rung;
+  int code = 0;
+  CUDA_TRY(cudaMemcpy(&code, s->a.err_code + p, sizeof(int), cudaMemcpyDeviceToHost));
+  s->failed = true;
+  if (err) {
+    memset(err, 0, sizeof(*err));
+    err->code = code; err->rung = rung; err->param = param;
+    err->iteration = (param < 0) ? 0 : launch_iter0 + it;
+    err->chain = s->cfg.chain_offset + chain;
+    for (int i = 0; i < s->D && i < 64; ++i)
+      cudaMemcpy(&err->theta[i], s->a.err_theta + (long long)i * s->P + p, sizeof(double), cudaMemcpyDeviceToHost);
+    std::string th;
+    for (int i = 0; i < s->D && i < 8; ++i) { char b[40]; snprintf(b, sizeof(b), "%s%.6g", i ? " " : "", err->theta[i]); th += b; }
+    snprintf(err->message, sizeof(err->message), "%s (chain %lld, rung %d, parameter %d, iteration %d; theta = %s%s)",
+             code_message(code), (long long)err->chain + 1, rung + 1, param + 1, err->iteration, th.c_str(),
+             s->D > 8 ? " ..." : "");
+  }
+  return code ? code : DRJ_ERR_CUDA;
+}
+
+static int validate(const drj_config* c, const drj_model* m, const drj_list* data, drj_error* err) {
+  if (!c || !m) return set_err(err, DRJ_ERR_ARG, "NULL config or model");
+  if (c->abi_version != DRJ_ABI_VERSION) return set_err(err, DRJ_ERR_ARG, "ABI version mismatch (%d != %d)", c->abi_version, DRJ_ABI_VERSION);
+  if (c->d < 1 || c->chains < 1 || c->rungs < 1 || c->burnin < 1 || c->samples < 1 || c->n_block < 1)
+    return set_err(err, DRJ_ERR_ARG, "d, chains, rungs, burnin, samples and n_block must be positive");
+  if (c->d != m->D || c->n_block != m->NBLOCK)
+    return set_err(err, DRJ_ERR_MODEL, "model '%s' has d=%d, n_block=%d but the config has d=%d, n_block=%d", m->name.c_str(),
+                   m->D, m->NBLOCK, c->d, c->n_block);
+  if (c->rungs > DRJ_NT) return set_err(err, DRJ_ERR_ARG, "rungs > %d not supported", DRJ_NT);
+  if (c->d > 1022) return set_err(err, DRJ_ERR_ARG, "d > 1022 not supported");
+  if (c->chains >= (1 << 24)) return set_err(err, DRJ_ERR_ARG, "more than 2^24-1 chains per call: shard the run");
+  if (!(c->target_acceptance >= 0.0 && c->target_acceptance <= 1.0)) return set_err(err, DRJ_ERR_ARG, "target_acceptance must be in [0,1]");
+  if (!c->theta_min || !c->theta_max || !c->trans_type || !c->skip_param || !c->block_ptr || !c->block_idx ||
+      !c->beta_raised || !c->theta_init)
+    return set_err(err, DRJ_ERR_ARG, "NULL array in config");
+  for (int i = 0; i < c->d; ++i) {
+    if (c->trans_type[i] < 0 || c->trans_type[i] > 3) return set_err(err, DRJ_ERR_TRANS_TYPE, "trans_type invalid");
+    for (int j = c->block_ptr[i]; j < c->block_ptr[i + 1]; ++j)
+      if (c->block_idx[j] < 1 || c->block_idx[j] > c->n_block) return set_err(err, DRJ_ERR_ARG, "block id out of range");
+  }
+  for (int r = 0; r < c->rungs; ++r) {
+    if (!(c->beta_raised[r] >= 0.0 && c->beta_raised[r] <= 1.0)) return set_err(err, DRJ_ERR_ARG, "beta_raised must be in [0,1]");
+    if (r > 0 && !(c->beta_raised[r] > c->beta_raised[r - 1])) return set_err(err, DRJ_ERR_ARG, "beta_raised must be increasing");
+  }
+  if (c->beta_raised[c->rungs - 1] != 1.0) return set_err(err, DRJ_ERR_ARG, "last beta_raised must be 1");
+  if (c->rng_mode == DRJ_RNG_REPLAY && !c->replay_uniforms) return set_err(err, DRJ_ERR_ARG, "replay mode needs replay_uniforms");
+  if (c->rng_mode != DRJ_RNG_REPLAY && c->rng_mode != DRJ_RNG_PHILOX) return set_err(err, DRJ_ERR_ARG, "unknown rng_mode");
+  if (m->datum_form && (!data || data->n_items < 1)) return set_err(err, DRJ_ERR_ARG, "model '%s' needs a data item", m->name.c_str());
+  return DRJ_OK;
+}
+
+extern "C" void drj_session_destroy(drj_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->cfg.device);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_model* model, const drj_list* data,
+                               const drj_list* misc, drj_error* err) {
+  s->cfg = *cfg;
+  s->model = model;
+  s->t_create = wall_now();
+  const int D = s->D = cfg->d, B = s->B = cfg->n_block, R = s->R = cfg->rungs, C = s->C = cfg->chains;
+  const long long P = s->P = (long long)C * R;
+  s->Ppt = cfg->store_pt ? P : C;
+  s->Pth = cfg->save_hot_draws ? P : C;
+  s->T_total = cfg->burnin - 1 + cfg->samples;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { cudaGetLastError(); return set_err(err, DRJ_ERR_CUDA, "no CUDA device %d", cfg->device); }
+  CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&s->ev0));
+  CUDA_TRY(cudaEventCreate(&s->ev1));
+  if (model->jit && !load_driver_api()) return set_err(err, DRJ_ERR_CUDA, "CUDA driver entry points unavailable");
+
+  // ---- launch geometry: all rungs of a chain in one CTA, as many chains per CTA as fit in DRJ_NT
+  // threads, but no more than needed to give every SM a few CTAs
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  const int max_cpc = std::max(1, DRJ_NT / R);
+  int cpc = cfg->chains_per_cta > 0 ? std::min(cfg->chains_per_cta, max_cpc) : max_cpc;
+  if (cfg->chains_per_cta <= 0 && !(model->datum_form)) {
+    // generic models do not share data tiles: prefer more, smaller CTAs when chains are few
+    const long long want_ctas = 4LL * prop.multiProcessorCount;
+    const int fit = (int)std::max<long long>(1, (C + want_ctas - 1) / want_ctas);
+    cpc = std::min(cpc, fit);
+  }
+  s->cpc = cpc;
+  s->nthreads = std::min(DRJ_NT, ((cpc * R + 31) / 32) * 32);
+  s->grid = (C + cpc - 1) / cpc;
+
+  // ---- sizes and the memory check
+  s->d_free = 0;
+  std::vector<int> free_slot(D);
+  for (int i = 0; i < D; ++i) free_slot[i] = cfg->skip_param[i] ? -1 : s->d_free++;
+  const long long U = 3LL * s->d_free * R + ((cfg->coupling_on && R > 1) ? (R - 1) : 0);
+  const double bytes_final = 8.0 * ((double)s->Ppt * 2 + (double)s->Pth * D) * ((double)cfg->burnin + cfg->samples);
+  const double bytes_state = 8.0 * (double)P * (6.0 * D + B + 4);
+  const double bytes_replay = cfg->rng_mode == DRJ_RNG_REPLAY ? 8.0 * (double)C * s->T_total * U : 0.0;
+  const double ring_row = 8.0 * ((double)s->Ppt * 2 + (double)s->Pth * D);
+  int tb = cfg->iters_per_launch > 0 ? cfg->iters_per_launch : (int)std::min(1024.0, std::max(1.0, 268435456.0 / ring_row));
+  tb = std::max(1, std::min(tb, std::max(1, s->T_total)));
+  tb = std::min(tb, (1 << 20) - 1);
+  s->tb = tb;
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const double need = bytes_final + bytes_state + bytes_replay + ring_row * tb + 64e6;
+  if (need > 0.92 * (double)free_b)
+    return set_err(err, DRJ_ERR_MEMORY,
+                   "run needs %.1f GB of device memory (outputs %.1f GB) but %.1f GB are free: reduce iterations, "
+                   "chains per call, or turn off store_pt / save_hot_draws",
+                   need / 1e9, bytes_final / 1e9, (double)free_b / 1e9);
+
+  // ---- uploads
+  DrjKernelArgs& a = s->a;
+  memset(&a, 0, sizeof(a));
+  a.chains = C; a.rungs = R; a.chains_per_cta = cpc; a.coupling_on = cfg->coupling_on ? 1 : 0;
+  a.save_hot_draws = cfg->save_hot_draws ? 1 : 0; a.store_pt = cfg->store_pt ? 1 : 0;
+  a.rng_mode = cfg->rng_mode; a.d_free = s->d_free;
+  a.use_tma = (cfg->flags & DRJ_FLAG_NO_TMA) ? 0 : 1;
+  if (const char* e = getenv("DRJ_NO_TMA")) if (e[0] == '1') a.use_tma = 0;
+  a.chain_offset = cfg->chain_offset; a.seed = cfg->seed; a.target_acceptance = cfg->target_acceptance; a.P = P;
+  CUDA_TRY(upload(s, &a.theta_min, cfg->theta_min, D));
+  CUDA_TRY(upload(s, &a.theta_max, cfg->theta_max, D));
+  CUDA_TRY(upload(s, &a.trans_type, cfg->trans_type, D));
+  CUDA_TRY(upload(s, &a.free_slot, free_slot.data(), D));
+  CUDA_TRY(upload(s, &a.block_ptr, cfg->block_ptr, D + 1));
+  CUDA_TRY(upload(s, &a.block_idx, cfg->block_idx, cfg->block_ptr[D]));
+  CUDA_TRY(upload(s, &a.beta_raised, cfg->beta_raised, R));
+  CUDA_TRY(upload(s, &a.theta_init, cfg->theta_init, (size_t)C * D));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));  // free_slot is a local
+  CUDA_TRY(upload_list(s, data, &a.data));
+  CUDA_TRY(upload_list(s, misc, &a.misc));
+  if (cfg->rng_mode == DRJ_RNG_REPLAY) {
+    CUDA_TRY(upload(s, &a.replay, cfg->replay_uniforms, (size_t)C * s->T_total * U));
+    a.replay_T = s->T_total; a.replay_U = U;
+  }
+  // ---- state
+  CUDA_TRY(dalloc(s, &a.theta, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &a.phi, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &a.logbw, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &a.bw_index, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &a.adj_lo, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &a.adj_hi, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &a.ll_block, (size_t)B * P));
+  CUDA_TRY(dalloc(s, &a.ll, (size_t)P));
+  CUDA_TRY(dalloc(s, &a.lp, (size_t)P));
+  CUDA_TRY(dalloc(s, &a.accept, (size_t)P));
+  CUDA_TRY(dalloc(s, &s->acc_b, (size_t)P));
+  CUDA_TRY(dalloc(s, &s->mc_b, (size_t)C * std::max(R - 1, 1)));
+  CUDA_TRY(dalloc(s, &s->mc_s, (size_t)C * std::max(R - 1, 1)));
+  CUDA_TRY(cudaMemsetAsync(s->mc_b, 0, sizeof(int) * (size_t)C * std::max(R - 1, 1), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->mc_s, 0, sizeof(int) * (size_t)C * std::max(R - 1, 1), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->acc_b, 0, sizeof(int) * (size_t)P, s->stream));
+  a.mc_accept = s->mc_b;
+  CUDA_TRY(dalloc(s, &a.err_code, (size_t)P));
+  CUDA_TRY(dalloc(s, &a.err_theta, (size_t)D * P));
+  CUDA_TRY(dalloc(s, &s->err_key, 1));
+  a.err_key = s->err_key;
+  CUDA_TRY(cudaMemsetAsync(a.err_code, 0, sizeof(int) * (size_t)P, s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->err_key, 0xFF, sizeof(unsigned long long), s->stream));
+  // ---- rings and final outputs
+  CUDA_TRY(dalloc(s, &a.ring_ll, (size_t)tb * s->Ppt));
+  CUDA_TRY(dalloc(s, &a.ring_lp, (size_t)tb * s->Ppt));
+  CUDA_TRY(dalloc(s, &a.ring_theta, (size_t)tb * D * s->Pth));
+  CUDA_TRY(dalloc(s, &s->fin_ll_b, (size_t)s->Ppt * cfg->burnin));
+  CUDA_TRY(dalloc(s, &s->fin_lp_b, (size_t)s->Ppt * cfg->burnin));
+  CUDA_TRY(dalloc(s, &s->fin_th_b, (size_t)s->Pth * cfg->burnin * D));
+  CUDA_TRY(dalloc(s, &s->fin_ll_s, (size_t)s->Ppt * cfg->samples));
+  CUDA_TRY(dalloc(s, &s->fin_lp_s, (size_t)s->Ppt * cfg->samples));
+  CUDA_TRY(dalloc(s, &s->fin_th_s, (size_t)s->Pth * cfg->samples * D));
+
+  // ---- Particle::init + init_like for every chain x rung, row 0 of the burn-in outputs
+  a.n_iter = 1; a.iter0 = 0;
+  int rc = launch_model_kernel(s, false, err);
+  if (rc) return rc;
+  s->aux_launches++;
+  if ((rc = flush_ring(s, 1, false, 0, err))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if ((rc = check_device_error(s, 0, err))) return rc;
+  if (cfg->burnin == 1) a.mc_accept = s->mc_s;  // no burn-in updates: straight into the sampling phase
+  return DRJ_OK;
+}
+
+extern "C" int drj_session_create(const drj_config* cfg, const drj_model* model, const drj_list* data,
+                                  const drj_list* misc, drj_session** out, drj_error* err) {
+  if (!out) return set_err(err, DRJ_ERR_ARG, "NULL out");
+  *out = nullptr;
+  int rc = validate(cfg, model, data, err);
+  if (rc) return rc;
+  drj_session* s = new drj_session();
+  rc = session_create_impl(s, cfg, model, data, misc, err);
+  if (rc) { drj_session_destroy(s); return rc; }
+  *out = s;
+  return DRJ_OK;
+}
+
+extern "C" int drj_session_advance(drj_session* s, int n_iter, float* kernel_ms, drj_error* err) {
+  if (!s) return set_err(err, DRJ_ERR_ARG, "NULL session");
+  if (s->failed) return set_err(err, DRJ_ERR_ARG, "session already failed");
+  if (kernel_ms) *kernel_ms = 0.f;
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  const int nb = s->cfg.burnin - 1;  // burn-in updates
+  int left = std::min(n_iter, s->T_total - s->t_done);
+  while (left > 0) {
+    const bool sampling = s->t_done >= nb;
+    const int phase_left = sampling ? (s->T_total - s->t_done) : (nb - s->t_done);
+    const int nt = std::min(std::min(left, phase_left), s->tb);
+    s->a.n_iter = nt;
+    s->a.iter0 = s->t_done + 1;
+    s->a.mc_accept = sampling ? s->mc_s : s->mc_b;
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    int rc = launch_model_kernel(s, true, err);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    s->sweep_launches++;
+    // burn-in row index = update index (row 0 = initial values); sampling column = t - burnin
+    const int col0 = sampling ? (s->t_done - nb) : (s->t_done + 1);
+    if ((rc = flush_ring(s, nt, sampling, col0, err))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (kernel_ms) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+      *kernel_ms += ms;
+    }
+    if ((rc = check_device_error(s, s->t_done + 1, err))) return rc;
+    s->t_done += nt;
+    left -= nt;
+    if (!sampling && s->t_done == nb) {
+      // end of burn-in: keep the counts, reset accept_count of all rungs (main.cpp:208-210)
+      CUDA_TRY(cudaMemcpyAsync(s->acc_b, s->a.accept, sizeof(int) * (size_t)s->P, cudaMemcpyDeviceToDevice, s->stream));
+      CUDA_TRY(cudaMemsetAsync(s->a.accept, 0, sizeof(int) * (size_t)s->P, s->stream));
+    }
+  }
+  return DRJ_OK;
+}
+
+extern "C" int drj_session_iterations_done(const drj_session* s) { return s ? s->t_done + 1 : 0; }
+
+extern "C" int drj_session_launches(const drj_session* s, int64_t* sweep_launches, int64_t* aux_launches) {
+  if (!s) return DRJ_ERR_ARG;
+  if (sweep_launches) *sweep_launches = s->sweep_launches;
+  if (aux_launches) *aux_launches = s->aux_launches;
+  return DRJ_OK;
+}
+
+extern "C" int drj_session_download(drj_session* s, drj_output* out, drj_error* err) {
+  if (!s || !out) return set_err(err, DRJ_ERR_ARG, "NULL session or output");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const drj_config& c = s->cfg;
+  const size_t nb = c.burnin, ns = c.samples;
+#define D2H(dst, src, n) \
+  if (dst) CUDA_TRY(cudaMemcpy(dst, src, (n), cudaMemcpyDeviceToHost))
+  D2H(out->loglike_burnin, s->fin_ll_b, sizeof(double) * s->Ppt * nb);
+  D2H(out->logprior_burnin, s->fin_lp_b, sizeof(double) * s->Ppt * nb);
+  D2H(out->theta_burnin, s->fin_th_b, sizeof(double) * s->Pth * nb * s->D);
+  D2H(out->loglike_sampling, s->fin_ll_s, sizeof(double) * s->Ppt * ns);
+  D2H(out->logprior_sampling, s->fin_lp_s, sizeof(double) * s->Ppt * ns);
+  D2H(out->theta_sampling, s->fin_th_s, sizeof(double) * s->Pth * ns * s->D);
+  if (s->R > 1) {
+    D2H(out->mc_accept_burnin, s->mc_b, sizeof(int) * (size_t)s->C * (s->R - 1));
+    D2H(out->mc_accept_sampling, s->mc_s, sizeof(int) * (size_t)s->C * (s->R - 1));
+  }
+  D2H(out->accept_burnin, s->acc_b, sizeof(int) * (size_t)s->P);
+  D2H(out->accept_sampling, s->a.accept, sizeof(int) * (size_t)s->P);
+#undef D2H
+  if (out->bw_final) {
+    double* tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * (size_t)s->P * s->D));
+    drj_export_bw<<<(unsigned)((s->P + 255) / 256), 256, 0, s->stream>>>(s->a.logbw, s->P, s->D, tmp);
+    s->aux_launches++;
+    cudaError_t e = cudaMemcpyAsync(out->bw_final, tmp, sizeof(double) * (size_t)s->P * s->D, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    CUDA_TRY(e);
+  }
+  if (out->t_diff) {
+    const double dt = (wall_now() - s->t_create) / std::max(1, s->C);
+    for (int ch = 0; ch < s->C; ++ch) out->t_diff[ch] = dt;
+  }
+  return DRJ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the drop-in entry
+// ------------------------------------------------------------------------------------------------
+extern "C" int drj_run_mcmc(const drj_config* cfg, const drj_model* model, const drj_list* data, const drj_list* misc,
+                            drj_output* out, drj_progress_fn progress, void* progress_user, drj_error* err) {
+  if (err) memset(err, 0, sizeof(*err));
+  if (!out) return set_err(err, DRJ_ERR_ARG, "NULL output");
+  drj_session* s = nullptr;
+  int rc = drj_session_create(cfg, model, data, misc, &s, err);
+  if (rc) return rc;
+  const int nb = cfg->burnin - 1;
+  // burn-in then sampling, in ~1 % batches when a progress hook is given (main.cpp:181-189, 241-249)
+  for (int phase = 0; phase < 2 && rc == DRJ_OK; ++phase) {
+    const int total = phase == 0 ? nb : cfg->samples;
+    const int step = progress ? std::max(1, (total + 99) / 100) : std::max(total, 1);
+    for (int done = 0; done < total && rc == DRJ_OK;) {
+      const int n = std::min(step, total - done);
+      rc = drj_session_advance(s, n, nullptr, err);
+      done += n;
+      if (rc == DRJ_OK && progress && progress(progress_user, phase, done + (phase == 0 ? 1 : 0), phase == 0 ? cfg->burnin : cfg->samples))
+        rc = set_err(err, DRJ_ERR_INTERRUPT, "interrupted by the progress callback");
+    }
+  }
+  if (rc == DRJ_OK) rc = drj_session_download(s, out, err);
+  drj_session_destroy(s);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probe
+// ------------------------------------------------------------------------------------------------
+extern "C" int drj_fp64_peak_tflops(int device, double* tflops, drj_error* err) {
+  if (!tflops) return set_err(err, DRJ_ERR_ARG, "NULL tflops");
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return set_err(err, DRJ_ERR_CUDA, "no CUDA device %d", device); }
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    drj_fp64_probe<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(out); return set_err(err, DRJ_ERR_CUDA, "probe failed: %s", cudaGetErrorString(e)); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return DRJ_OK;
+}

@@ -1,0 +1,232 @@
+// drj_models.cuh -- built-in model library: CUDA restatements of every likelihood / prior the
+// reference ships (inst/extdata/*.cpp, inst/extdata/checks/*.cpp, tests/testthat/test_input_files,
+// vignettes/getting_model_fits.Rmd) written against the device model contract of drj_sampler.cuh.
+// Parameters arrive as `const double* theta` in df_params order (the reference passes a named
+// NumericVector, src/main.cpp:11); `data` / `misc` are the flattened named lists; the current block
+// (misc["block"], src/Particle.h:110) is the `block` argument.
+#pragma once
+#include "drj_sampler.cuh"
+
+// per-datum form of  sum_i R::dnorm(x_i, mean, sd, log=TRUE):  z = x*(1/sd) - mean/sd  (1 FMA),
+// acc = z*z + acc (1 FMA); constants hoisted out of the data loop.
+struct DrjNormConsts {
+  double a, b, lognorm;
+};
+__device__ __forceinline__ bool drj_norm_prepare(double mean, double sd, DrjNormConsts& k) {
+  const double inv = 1.0 / sd;
+  k.a = inv;
+  k.b = -mean * inv;
+  k.lognorm = DRJ_LN_SQRT_2PI + log(sd);
+  // outside this range R::dnorm's edge-case branches matter: use the exact serial evaluation
+  return (sd > 1e-150) && (sd < 1e150) && (fabs(mean) < 1e150);
+}
+__device__ __forceinline__ double drj_norm_datum(const DrjNormConsts& k, double x, double acc) {
+  const double z = fma(x, k.a, k.b);
+  return fma(z, z, acc);
+}
+__device__ __forceinline__ double drj_norm_finish(const DrjNormConsts& k, double acc, long long n) {
+  return -((double)n * k.lognorm + 0.5 * acc);
+}
+__device__ __forceinline__ double drj_norm_serial(const double* x, long long n, double mean, double sd) {
+  double ret = 0.0;
+  for (long long i = 0; i < n; ++i) ret += R::dnorm(x[i], mean, sd, 1);
+  return ret;
+}
+
+// inst/extdata/example_loglike_logprior.cpp:5-35 -- params (mu, sigma), data$x  (K1, K5)
+struct DrjModelExample {
+  static constexpr int D = 2, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = true;
+  typedef DrjNormConsts Consts;
+  __device__ static __forceinline__ int datum_item(int) { return 0; }
+  __device__ static __forceinline__ bool prepare(const double* th, const DrjList&, int, Consts& k) {
+    return drj_norm_prepare(th[0], th[1], k);
+  }
+  __device__ static __forceinline__ double datum(const Consts& k, double x, double acc) { return drj_norm_datum(k, x, acc); }
+  __device__ static __forceinline__ double finish(const Consts& k, double acc, long long n) { return drj_norm_finish(k, acc, n); }
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
+    return drj_norm_serial(data.item(0), data.len(0), th[0], th[1]);
+  }
+  __device__ static __forceinline__ double logprior(const double* th, const DrjList&) {
+    return -log(20.0) + R::dlnorm(th[1], 0.0, 1.0, 1);
+  }
+};
+
+// same model, likelihood evaluated exactly as the reference does (serial R::dnorm per datum)
+struct DrjModelExampleExact : DrjModelExample {
+  static constexpr bool DATUM_FORM = false;
+};
+
+// inst/extdata/coupling_loglike_logprior.cpp:5-37 -- params (alpha, beta, epsilon), data$x
+struct DrjModelCoupling {
+  static constexpr int D = 3, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = true;
+  typedef DrjNormConsts Consts;
+  __device__ static __forceinline__ int datum_item(int) { return 0; }
+  __device__ static __forceinline__ bool prepare(const double* th, const DrjList&, int, Consts& k) {
+    return drj_norm_prepare(th[0] * th[0] * th[1] + th[2], 1.0, k);
+  }
+  __device__ static __forceinline__ double datum(const Consts& k, double x, double acc) { return drj_norm_datum(k, x, acc); }
+  __device__ static __forceinline__ double finish(const Consts& k, double acc, long long n) { return drj_norm_finish(k, acc, n); }
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
+    return drj_norm_serial(data.item(0), data.len(0), th[0] * th[0] * th[1] + th[2], 1.0);
+  }
+  __device__ static __forceinline__ double logprior(const double* th, const DrjList&) {
+    return -log(20.0) - log(10.0) + R::dnorm(th[2], 0.0, 1.0, 1);
+  }
+};
+
+// inst/extdata/checks/normal_loglike_logprior.cpp:5-20 -- params (mu), data$x, sd 1
+struct DrjModelNormalMu {
+  static constexpr int D = 1, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = true;
+  typedef DrjNormConsts Consts;
+  __device__ static __forceinline__ int datum_item(int) { return 0; }
+  __device__ static __forceinline__ bool prepare(const double* th, const DrjList&, int, Consts& k) {
+    return drj_norm_prepare(th[0], 1.0, k);
+  }
+  __device__ static __forceinline__ double datum(const Consts& k, double x, double acc) { return drj_norm_datum(k, x, acc); }
+  __device__ static __forceinline__ double finish(const Consts& k, double acc, long long n) { return drj_norm_finish(k, acc, n); }
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
+    return drj_norm_serial(data.item(0), data.len(0), th[0], 1.0);
+  }
+  __device__ static __forceinline__ double logprior(const double*, const DrjList&) { return 0.0; }
+};
+
+// inst/extdata/checks/doublewell_loglike_logprior.cpp:5-16 -- params (mu, gamma), no data  (K2)
+struct DrjModelDoubleWell {
+  static constexpr int D = 2, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static __forceinline__ double loglike(const double* th, const DrjList&, const DrjList&, int) {
+    const double mu = th[0], gamma = th[1];
+    return -gamma * (mu * mu - 1.0) * (mu * mu - 1.0);
+  }
+  __device__ static __forceinline__ double logprior(const double*, const DrjList&) { return 0.0; }
+};
+
+// inst/extdata/checks/multilevel_loglike_logprior.cpp:5-33 generalised to G groups (the shipped
+// file has G = 5; K4 uses G = 50): params mu_1..mu_G, blocks 1..G = data groups, block G+1 = global
+template <int G>
+struct DrjModelMultilevel {
+  static constexpr int D = G, NBLOCK = G + 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int block) {
+    double ret = 0.0;
+    if (block == G + 1) {
+      for (int i = 0; i < G; ++i) ret += R::dnorm(th[i], 0.0, 1.0, 1);
+    } else {
+      const double* x = data.item(block - 1);
+      const long long n = data.len(block - 1);
+      const double mu = th[block - 1];
+      for (long long i = 0; i < n; ++i) ret += R::dnorm(x[i], mu, 1.0, 1);
+    }
+    return ret;
+  }
+  __device__ static __forceinline__ double logprior(const double*, const DrjList&) { return 0.0; }
+};
+
+// inst/extdata/blocks_loglike_logprior.cpp:5-58 with G groups (shipped: G = 6):
+// params mu_1..mu_G, sigma, phi, tau
+template <int G>
+struct DrjModelBlocks {
+  static constexpr int D = G + 3, NBLOCK = G + 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int block) {
+    const double sigma = th[G], phi = th[G + 1], tau = th[G + 2];
+    double ret = 0.0;
+    if (block == G + 1) {
+      for (int i = 0; i < G; ++i) ret += R::dnorm(th[i], phi, tau, 1);
+    } else {
+      const double* x = data.item(block - 1);
+      const long long n = data.len(block - 1);
+      const double mu = th[block - 1];
+      for (long long i = 0; i < n; ++i) ret += R::dnorm(x[i], mu, sigma, 1);
+    }
+    return ret;
+  }
+  __device__ static double logprior(const double* th, const DrjList&) {
+    return R::dgamma(th[G], 0.01, 100.0, 1) + R::dnorm(th[G + 1], 0.0, 1000.0, 1) + R::dgamma(th[G + 2], 0.01, 100.0, 1);
+  }
+};
+
+// inst/extdata/checks/returnprior_loglike_logprior.cpp:5-18:
+// params (real_line, neg_line, pos_line, unit_interval)
+struct DrjModelReturnPrior {
+  static constexpr int D = 4, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static __forceinline__ double loglike(const double*, const DrjList&, const DrjList&, int) { return 0.0; }
+  __device__ static double logprior(const double* th, const DrjList&) {
+    return R::dnorm(th[0], 0.0, 1.0, 1) + R::dgamma(-th[1], 5.0, 5.0, 1) + R::dgamma(th[2], 5.0, 5.0, 1) +
+           R::dbeta(th[3], 3.0, 3.0, 1);
+  }
+};
+
+// tests/testthat/test_input_files/loglike_logprior.cpp:6-50 -- (mu, sigma) with the underflow clamp
+template <bool LIKE, bool PRIOR>
+struct DrjModelTestFile {
+  static constexpr int D = 2, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
+    if (!LIKE) return 0.0;
+    double ret = drj_norm_serial(data.item(0), data.len(0), th[0], th[1]);
+    if (!isfinite(ret)) ret = -(DRJ_DBL_MAX / 100.0);
+    return ret;
+  }
+  __device__ static double logprior(const double* th, const DrjList&) {
+    if (!PRIOR) return 0.0;
+    double ret = R::dnorm(th[0], 6.0, 0.1, 1) + R::dnorm(th[1], 1.0, 0.1, 1);
+    if (!isfinite(ret)) ret = -(DRJ_DBL_MAX / 100.0);
+    return ret;
+  }
+};
+
+// vignettes/getting_model_fits.Rmd:72-104 -- params (N_0, r, N_max), data (pop, time)  (K3)
+struct DrjModelLogistic {
+  static constexpr int D = 3, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
+    const double N_0 = th[0], r = th[1], N_max = th[2];
+    const double K = N_max * r / (r - 1.0);
+    const double* pop = data.item(0);
+    const double* time = data.item(1);
+    const int n = (int)data.len(0);
+    // observation times are increasing in the shipped data; walk the 100-step map once and pick
+    // off the observed steps (falls back to re-walking if a time goes backwards)
+    double ret = 0.0;
+    double x = N_0;
+    int step = 1;  // x == x[step], 1-based as in the R code
+    for (int j = 0; j < n; ++j) {
+      const int tj = (int)time[j];
+      if (tj < step) { x = N_0; step = 1; }
+      for (; step < tj; ++step) x = r * x * (1.0 - x / K);
+      ret += R::dpois(pop[j], x, 1);
+    }
+    return ret;
+  }
+  __device__ static double logprior(const double* th, const DrjList&) {
+    return R::dunif(th[0], 1.0, 100.0, 1) + R::dunif(th[1], 1.0, 2.0, 1) + R::dunif(th[2], 50.0, 200.0, 1);
+  }
+};
+
+// tests/testthat/test-Inf_checks_work.R:14-94 -- constant returns: loglike = misc[[1]], logprior = misc[[2]]
+struct DrjModelConst {
+  static constexpr int D = 1, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static __forceinline__ double loglike(const double*, const DrjList&, const DrjList& misc, int) { return misc.scalar(0); }
+  __device__ static __forceinline__ double logprior(const double*, const DrjList& misc) { return misc.scalar(1); }
+};
+
+// tests/testthat/test-Inf_checks_work.R:162-169 and :221-228 -- -Inf over half the domain
+template <bool IN_LIKE>
+struct DrjModelHalfDomain {
+  static constexpr int D = 1, NBLOCK = 1;
+  static constexpr bool DATUM_FORM = false;
+  __device__ static __forceinline__ double loglike(const double* th, const DrjList&, const DrjList&, int) {
+    if (!IN_LIKE) return 0.0;
+    return (th[0] > 0.5) ? -DRJ_INF : 2.0;
+  }
+  __device__ static __forceinline__ double logprior(const double* th, const DrjList&) {
+    if (IN_LIKE) return 0.0;
+    return (th[0] > 0.5) ? -DRJ_INF : 2.0;
+  }
+};

@@ -1,0 +1,620 @@
+// drj_sampler.cuh -- the MCMC sweep kernels of drjacoby_b200 (sm_100a), templated on a model.
+//
+// What it replaces (reference, one call per chain, rungs serial):
+//   Particle::init / theta_to_phi / init_like    src/Particle.cpp:8-44,78-99, src/Particle.h:59-79
+//   Particle::update                             src/Particle.h:82-171
+//     propose_phi / phi_prop_to_theta_prop / get_adjustment   src/Particle.cpp:48-74,103-124
+//   coupling                                     src/main.cpp:282-344
+//   run_mcmc<T1,T2> iteration loop and storage   src/main.cpp:84-278
+//
+// B200 design (not a port): ONE thread owns ONE (chain, rung) particle and keeps its state in
+// registers across all iterations of a launch; all rungs of a chain sit in one CTA so the
+// Metropolis-coupling pass is a shared-memory pass; every chain x rung advances in lock-step, so a
+// per-datum likelihood is evaluated CTA-wide: data tiles are staged ONCE per CTA into shared
+// memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier, double buffered) and every thread
+// walks the tile with broadcast LDS, accumulating its own sum in index order.  Samples go to
+// [iteration][particle] rings (coalesced) and are transposed on the device into the reference's
+// per-chain layout.
+//
+// Compiled by nvcc (built-in models) and by NVRTC (user models): no standard headers here.
+#pragma once
+#include "drj_device.cuh"
+
+#ifndef DRJ_NT
+#define DRJ_NT 256      // max threads per CTA
+#endif
+#ifndef DRJ_TILE
+#define DRJ_TILE 2048   // doubles per data tile (16 KB); two tiles are resident per CTA
+#endif
+#define DRJ_EXCH 4      // doubles per thread exchanged per shared-memory pass during a rung swap
+
+#ifndef DRJACOBY_B200_H  // the host side takes these from include/drjacoby_b200.h
+enum {
+  DRJ_OK = 0,
+  DRJ_ERR_INIT_NEGINF = 1,   // Particle.h:75-78
+  DRJ_ERR_LOGLIKE_BAD = 2,   // Particle.h:121-124
+  DRJ_ERR_LOGPRIOR_BAD = 3,  // Particle.h:125-128
+  DRJ_ERR_TRANS_TYPE = 4     // Particle.cpp:71,95,120
+};
+#endif
+
+struct DrjKernelArgs {
+  int chains;          // chains in this shard
+  int rungs;
+  int chains_per_cta;
+  int n_iter;          // iterations in this launch
+  int iter0;           // global update index t (1-based) of the first iteration of this launch
+  int coupling_on;
+  int save_hot_draws;
+  int store_pt;        // ring holds loglike/logprior of all rungs (1) or of the cold rung only (0)
+  int rng_mode;        // 0 Philox, 1 replay
+  int d_free;
+  int use_tma;
+  int pad0;
+  long long chain_offset;     // global id of chain 0 (Philox counter)
+  unsigned long long seed;
+  double target_acceptance;
+  long long P;                // chains * rungs
+  // per-parameter metadata, device arrays
+  const double* theta_min;    // [D]
+  const double* theta_max;    // [D]
+  const int* trans_type;      // [D]
+  const int* free_slot;       // [D] index among free parameters, -1 = skip_param
+  const int* block_ptr;       // [D+1]
+  const int* block_idx;       // 1-based
+  const double* beta_raised;  // [R]
+  const double* theta_init;   // [chains][D]
+  DrjList data;
+  DrjList misc;
+  // replay uniforms [chains][T][U]
+  const double* replay;
+  long long replay_T;
+  long long replay_U;
+  // particle state, SoA [field][P]
+  double* theta;      // [D][P]
+  double* phi;        // [D][P]
+  double* logbw;      // [D][P]  log of the proposal bandwidth (Particle::bw)
+  int* bw_index;      // [D][P]
+  double* adj_lo;     // [D][P]  log(theta - min) of the current state
+  double* adj_hi;     // [D][P]  log(max - theta) of the current state
+  double* ll_block;   // [B][P]
+  double* ll;         // [P]
+  double* lp;         // [P]
+  int* accept;        // [P]
+  int* mc_accept;     // [chains][R-1]
+  // sample rings of this launch
+  double* ring_ll;    // [n_iter][P] or [n_iter][chains]
+  double* ring_lp;
+  double* ring_theta; // [n_iter][D][P] or [n_iter][D][chains]
+  // error slot
+  unsigned long long* err_key;  // packed (iteration-in-launch, chain, rung, param), atomicMin
+  int* err_code;                // [P] code of the particle's first error in this launch
+  double* err_theta;            // [D][P] offending theta'
+};
+
+// ------------------------------------------------------------------ TMA bulk copy + mbarrier
+__device__ __forceinline__ unsigned drj_smem_addr(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void drj_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(drj_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void drj_mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void drj_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(drj_smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void drj_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "DRJ_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DRJ_DONE;\n"
+      "bra DRJ_WAIT;\n"
+      "DRJ_DONE:\n"
+      "}\n" ::"r"(drj_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`
+__device__ __forceinline__ void drj_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
+                                             unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   drj_smem_addr(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(drj_smem_addr(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------ model traits helpers
+// A model is a struct with
+//   static constexpr int D, NBLOCK;  static constexpr bool DATUM_FORM;
+//   __device__ static double loglike(const double* theta, const DrjList& data, const DrjList& misc, int block);
+//   __device__ static double logprior(const double* theta, const DrjList& misc);
+// and, when DATUM_FORM (likelihood of `block` = finish(sum over data item datum_item(block))):
+//   struct Consts;  static bool prepare(theta, misc, block, Consts&)   (false = use loglike())
+//   static double datum(const Consts&, double x, double acc);  static double finish(const Consts&, double acc, long long n);
+//   static int datum_item(int block);
+
+template <class M, bool DF = M::DATUM_FORM>
+struct DrjTiles {  // no tiles for generic models
+  __device__ __forceinline__ void init(const DrjKernelArgs&) {}
+};
+
+template <class M>
+struct DrjTiles<M, true> {
+  double* buf;                 // [2][DRJ_TILE]
+  unsigned long long* full;    // [2] mbarriers
+  unsigned ph0, ph1;           // phase parity of each stage
+  bool resident;               // whole item lives in buf for the life of the kernel
+  bool tma;
+  __device__ __forceinline__ void init(const DrjKernelArgs& a) {
+    __shared__ __align__(128) double s_buf[2 * DRJ_TILE];
+    __shared__ __align__(8) unsigned long long s_full[2];
+    buf = s_buf;
+    full = s_full;
+    ph0 = ph1 = 0;
+    tma = a.use_tma != 0;
+    // single-item models keep the data resident when it fits the two tiles
+    const int item = M::datum_item(1);
+    const long long n = a.data.len(item);
+    resident = (M::NBLOCK == 1) && (n <= 2 * DRJ_TILE);
+    if (threadIdx.x == 0) {
+      drj_mbar_init(&full[0], 1);
+      drj_mbar_init(&full[1], 1);
+      drj_mbar_fence_init();
+    }
+    if (resident) {
+      const double* g = a.data.item(item);
+      for (long long j = threadIdx.x; j < n; j += blockDim.x) s_buf[j] = g[j];
+    }
+    __syncthreads();
+  }
+};
+
+// CTA-wide likelihood sweep: every thread evaluates ITS OWN theta against the SAME data item.
+// Must be called by all threads of the CTA (uniform control flow).  Each thread's sum runs in
+// index order (the reference's `ret +=` loop, inst/extdata/example_loglike_logprior.cpp:15-18).
+template <class M>
+__device__ __forceinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typename M::Consts& k,
+                                                 const double* __restrict__ g, long long n) {
+  double acc = 0.0;
+  if (T.resident) {
+    const double2* t2 = reinterpret_cast<const double2*>(T.buf);
+    const int n2 = (int)(n >> 1);
+#pragma unroll 8
+    for (int j = 0; j < n2; ++j) {
+      double2 v = t2[j];
+      acc = M::datum(k, v.x, acc);
+      acc = M::datum(k, v.y, acc);
+    }
+    if (n & 1) acc = M::datum(k, T.buf[n - 1], acc);
+    return acc;
+  }
+  const long long ntiles = (n + DRJ_TILE - 1) / DRJ_TILE;
+  const unsigned tile_bytes = DRJ_TILE * sizeof(double);
+  if (T.tma) {
+    // prologue: TMA engine fills both stages (the buffer is padded to whole tiles by the host)
+    if (threadIdx.x == 0) {
+      drj_mbar_expect_tx(&T.full[0], tile_bytes);
+      drj_bulk_g2s(T.buf, g, tile_bytes, &T.full[0]);
+      if (ntiles > 1) {
+        drj_mbar_expect_tx(&T.full[1], tile_bytes);
+        drj_bulk_g2s(T.buf + DRJ_TILE, g + DRJ_TILE, tile_bytes, &T.full[1]);
+      }
+    }
+    for (long long kt = 0; kt < ntiles; ++kt) {
+      const int s = (int)(kt & 1);
+      if (s == 0) { drj_mbar_wait(&T.full[0], T.ph0); T.ph0 ^= 1u; }
+      else        { drj_mbar_wait(&T.full[1], T.ph1); T.ph1 ^= 1u; }
+      const long long rem = n - kt * DRJ_TILE;
+      const int cnt = rem < DRJ_TILE ? (int)rem : DRJ_TILE;
+      const double2* t2 = reinterpret_cast<const double2*>(T.buf + s * DRJ_TILE);
+      if (cnt == DRJ_TILE) {
+#pragma unroll 8
+        for (int j = 0; j < DRJ_TILE / 2; ++j) {
+          double2 v = t2[j];
+          acc = M::datum(k, v.x, acc);
+          acc = M::datum(k, v.y, acc);
+        }
+      } else {
+        const double* t1 = T.buf + s * DRJ_TILE;
+        for (int j = 0; j < cnt; ++j) acc = M::datum(k, t1[j], acc);
+      }
+      __syncthreads();  // everyone is done with stage s before the engine refills it
+      if (threadIdx.x == 0 && kt + 2 < ntiles) {
+        drj_mbar_expect_tx(&T.full[s], tile_bytes);
+        drj_bulk_g2s(T.buf + s * DRJ_TILE, g + (kt + 2) * DRJ_TILE, tile_bytes, &T.full[s]);
+      }
+    }
+  } else {
+    // plain cooperative staging (debug / comparison path, selected with DRJ_NO_TMA=1)
+    for (long long kt = 0; kt < ntiles; ++kt) {
+      const long long rem = n - kt * DRJ_TILE;
+      const int cnt = rem < DRJ_TILE ? (int)rem : DRJ_TILE;
+      __syncthreads();
+      for (int j = threadIdx.x; j < cnt; j += blockDim.x) T.buf[j] = g[kt * DRJ_TILE + j];
+      __syncthreads();
+      for (int j = 0; j < cnt; ++j) acc = M::datum(k, T.buf[j], acc);
+    }
+  }
+  return acc;
+}
+
+template <class M>
+__device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const DrjKernelArgs& a,
+                                                   const double* theta, int block) {
+  typename M::Consts k;
+  const bool fast = M::prepare(theta, a.misc, block, k);
+  const int item = M::datum_item(block);
+  const long long n = a.data.len(item);
+  const double acc = drj_sweep_item<M>(T, k, a.data.item(item), n);  // uniform: all threads sweep
+  if (fast) return M::finish(k, acc, n);
+  return M::loglike(theta, a.data, a.misc, block);  // degenerate theta: exact serial evaluation
+}
+
+template <class M>
+__device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, false>&, const DrjKernelArgs& a,
+                                                   const double* theta, int block) {
+  return M::loglike(theta, a.data, a.misc, block);
+}
+
+// ------------------------------------------------------------------ error slot
+__device__ __forceinline__ void drj_report(const DrjKernelArgs& a, int code, int it, long long chain,
+                                           int r, int param, long long p, const double* theta, int D) {
+  if (a.err_code[p] != 0) return;  // keep the particle's first error
+  a.err_code[p] = code;
+  for (int i = 0; i < D; ++i) a.err_theta[(long long)i * a.P + p] = theta[i];
+  unsigned long long key = ((unsigned long long)(unsigned)it << 44) | ((unsigned long long)chain << 20) |
+                           ((unsigned long long)(unsigned)r << 10) | (unsigned long long)(unsigned)(param + 1);
+  atomicMin(a.err_key, key);
+}
+
+// ------------------------------------------------------------------ per-thread particle state
+template <class M>
+struct DrjState {
+  double theta[M::D], phi[M::D], logbw[M::D], alo[M::D], ahi[M::D];
+  int bwi[M::D];
+  double llb[M::NBLOCK], llb_p[M::NBLOCK];
+  double ll, lp;
+  int acc;
+};
+
+#define DRJ_UNROLL_N(N) ((N) <= 8 ? (N) : 1)
+
+// ------------------------------------------------------------------ init kernel body
+// Particle::init + theta_to_phi + init_like for every (chain, rung); writes state and row 0 of the
+// burn-in outputs (main.cpp:128-137).
+template <class M>
+__device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
+  constexpr int D = M::D, B = M::NBLOCK;
+  constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
+  const int R = a.rungs;
+  const int tid = threadIdx.x;
+  const int lc = tid / R, r = tid - lc * R;
+  const long long chain = (long long)blockIdx.x * a.chains_per_cta + lc;
+  const bool active = (lc < a.chains_per_cta) && (chain < a.chains);
+  const long long cc = active ? chain : 0;  // inactive threads shadow chain 0 (uniform control flow)
+  const long long p = cc * R + r;
+  const long long P = a.P;
+
+  DrjTiles<M> T;
+  T.init(a);
+
+  DrjState<M> s;
+  int err = 0;
+#pragma unroll UD
+  for (int i = 0; i < D; ++i) {
+    const double th = a.theta_init[cc * D + i];
+    const double tmin = a.theta_min[i], tmax = a.theta_max[i];
+    s.theta[i] = th;
+    s.alo[i] = 0.0;
+    s.ahi[i] = 0.0;
+    switch (a.trans_type[i]) {
+      case 0: s.phi[i] = th; break;
+      case 1: s.ahi[i] = log(tmax - th); s.phi[i] = s.ahi[i]; break;
+      case 2: s.alo[i] = log(th - tmin); s.phi[i] = s.alo[i]; break;
+      case 3: s.alo[i] = log(th - tmin); s.ahi[i] = log(tmax - th); s.phi[i] = s.alo[i] - s.ahi[i]; break;
+      default: err = DRJ_ERR_TRANS_TYPE; s.phi[i] = th; break;
+    }
+    s.logbw[i] = 0.0;  // bw = 1
+    s.bwi[i] = 1;
+  }
+#pragma unroll UB
+  for (int b = 0; b < B; ++b) s.llb[b] = 0.0;
+  // init_like: every block listed by every parameter (duplicates re-evaluated), Particle.h:62-68
+  for (int i = 0; i < D; ++i)
+    for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+      const int b = a.block_idx[j];
+      s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
+    }
+  s.ll = 0.0;
+#pragma unroll UB
+  for (int b = 0; b < B; ++b) s.ll += s.llb[b];
+  s.lp = M::logprior(s.theta, a.misc);
+  if (err == 0 && (s.ll == -DRJ_INF || s.lp == -DRJ_INF)) err = DRJ_ERR_INIT_NEGINF;
+
+  if (active) {
+    if (err) drj_report(a, err, 0, chain, r, -1, p, s.theta, D);
+#pragma unroll UD
+    for (int i = 0; i < D; ++i) {
+      const long long o = (long long)i * P + p;
+      a.theta[o] = s.theta[i]; a.phi[o] = s.phi[i]; a.logbw[o] = s.logbw[i];
+      a.adj_lo[o] = s.alo[i]; a.adj_hi[o] = s.ahi[i]; a.bw_index[o] = s.bwi[i];
+    }
+#pragma unroll UB
+    for (int b = 0; b < B; ++b) a.ll_block[(long long)b * P + p] = s.llb[b];
+    a.ll[p] = s.ll; a.lp[p] = s.lp; a.accept[p] = 0;
+    if (r < R - 1) a.mc_accept[chain * (R - 1) + r] = 0;
+    // row 0 of the burn-in outputs
+    if (a.store_pt) { a.ring_ll[p] = s.ll; a.ring_lp[p] = s.lp; }
+    else if (r == R - 1) { a.ring_ll[chain] = s.ll; a.ring_lp[chain] = s.lp; }
+    if (a.save_hot_draws) {
+      for (int i = 0; i < D; ++i) a.ring_theta[(long long)i * P + p] = s.theta[i];
+    } else if (r == R - 1) {
+      for (int i = 0; i < D; ++i) a.ring_theta[(long long)i * a.chains + chain] = s.theta[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sweep kernel body
+// n_iter iterations of: update every rung (Particle::update), store, Metropolis coupling.
+template <class M>
+__device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
+  constexpr int D = M::D, B = M::NBLOCK;
+  constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
+  const int R = a.rungs;
+  const int tid = threadIdx.x;
+  const int lc = tid / R, r = tid - lc * R;
+  const long long chain = (long long)blockIdx.x * a.chains_per_cta + lc;
+  const bool active = (lc < a.chains_per_cta) && (chain < a.chains);
+  const long long cc = active ? chain : 0;
+  const long long p = cc * R + r;
+  const long long P = a.P;
+  const int base = lc * R;  // first thread of this chain in the CTA
+
+  __shared__ double s_tmin[D], s_tmax[D];
+  __shared__ int s_trans[D], s_free[D];
+  __shared__ double s_x[DRJ_EXCH * DRJ_NT];  // rung-swap exchange buffer; s_x[0..NT) doubles as loglike
+  __shared__ double s_logu[DRJ_NT];
+  __shared__ short s_src[DRJ_NT];
+  __shared__ int s_mc[DRJ_NT];
+
+  for (int i = tid; i < D; i += blockDim.x) {
+    s_tmin[i] = a.theta_min[i]; s_tmax[i] = a.theta_max[i];
+    s_trans[i] = a.trans_type[i]; s_free[i] = a.free_slot[i];
+  }
+  s_mc[tid] = 0;
+
+  DrjTiles<M> T;
+  T.init(a);
+  __syncthreads();
+
+  // ---- load state into registers
+  DrjState<M> s;
+#pragma unroll UD
+  for (int i = 0; i < D; ++i) {
+    const long long o = (long long)i * P + p;
+    s.theta[i] = a.theta[o]; s.phi[i] = a.phi[o]; s.logbw[i] = a.logbw[o];
+    s.alo[i] = a.adj_lo[o]; s.ahi[i] = a.adj_hi[o]; s.bwi[i] = a.bw_index[o];
+  }
+#pragma unroll UB
+  for (int b = 0; b < B; ++b) { s.llb[b] = a.ll_block[(long long)b * P + p]; s.llb_p[b] = s.llb[b]; }
+  s.ll = a.ll[p]; s.lp = a.lp[p]; s.acc = a.accept[p];
+  const double beta = a.beta_raised[r];
+  const double target = a.target_acceptance;
+  const unsigned gchain_lo = (unsigned)(unsigned long long)(a.chain_offset + cc);
+  const unsigned gchain_hi = (unsigned)((unsigned long long)(a.chain_offset + cc) >> 32);
+  const unsigned k0 = (unsigned)a.seed, k1 = (unsigned)(a.seed >> 32);
+  const bool do_couple = a.coupling_on && R > 1;
+
+  for (int it = 0; it < a.n_iter; ++it) {
+    const int t = a.iter0 + it;  // global update index, 1-based
+    int err = 0;
+    const double* rp = a.rng_mode ? a.replay + (cc * a.replay_T + (t - 1)) * a.replay_U : nullptr;
+
+    // ================= Particle::update =================
+#pragma unroll UD
+    for (int i = 0; i < D; ++i) {
+      const int fs = s_free[i];
+      if (fs < 0) continue;  // skip_param: no RNG consumed (Particle.h:91-93)
+      double u1, u2, u3;
+      if (a.rng_mode) {
+        const double* q = rp + 3 * ((long long)r * a.d_free + fs);
+        u1 = q[0]; u2 = q[1]; u3 = q[2];
+      } else {
+        DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, ((unsigned)r << 16) | (unsigned)i, gchain_hi << 8, k0, k1);
+        u1 = drj_u32_to_unif(w.x); u2 = drj_u32_to_unif(w.y); u3 = drj_u32_to_unif(w.z);
+      }
+      // propose_phi
+      const double bw = exp(s.logbw[i]);
+      const double phi_p = drj_rnorm(s.phi[i], bw, u1, u2);
+      // phi_prop_to_theta_prop + get_adjustment
+      const double tmin = s_tmin[i], tmax = s_tmax[i];
+      double th_p, lo_p = 0.0, hi_p = 0.0, adj = 0.0;
+      switch (s_trans[i]) {
+        case 0: th_p = phi_p; break;
+        case 1: th_p = tmax - exp(phi_p); hi_p = log(tmax - th_p); adj = hi_p - s.ahi[i]; break;
+        case 2: th_p = exp(phi_p) + tmin; lo_p = log(th_p - tmin); adj = lo_p - s.alo[i]; break;
+        default: {
+          const double e = exp(phi_p);
+          th_p = (tmax * e + tmin) / (1.0 + e);
+          hi_p = log(tmax - th_p); lo_p = log(th_p - tmin);
+          adj = hi_p + lo_p - s.ahi[i] - s.alo[i];
+        } break;
+      }
+      const double th_cur = s.theta[i];
+      s.theta[i] = th_p;  // s.theta is theta_prop from here to the accept/reject
+      // likelihood of the blocks this parameter belongs to (Particle.h:107-112)
+      for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+        const int b = a.block_idx[j];
+        s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
+      }
+      double ll_p = 0.0;
+#pragma unroll UB
+      for (int b = 0; b < B; ++b) ll_p += s.llb_p[b];  // sequential, index order (misc.h:20-27)
+      const double lp_p = M::logprior(s.theta, a.misc);
+      // NaN / +Inf guard (Particle.h:121-128)
+      if (err == 0 && active) {
+        if (isnan(ll_p) || ll_p == DRJ_INF) err = DRJ_ERR_LOGLIKE_BAD;
+        else if (isnan(lp_p) || lp_p == DRJ_INF) err = DRJ_ERR_LOGPRIOR_BAD;
+        if (err) drj_report(a, err, it, chain, r, i, p, s.theta, D);
+      }
+      // Metropolis-Hastings (Particle.h:131-139)
+      double MH;
+      if (beta == 0.0) MH = (lp_p - s.lp) + adj;
+      else MH = beta * (ll_p - s.ll) + (lp_p - s.lp) + adj;
+      const bool accept = (log(u3) < MH) && (err == 0);
+      const double gain = rsqrt((double)s.bwi[i]);  // bw_stepsize = 1
+      if (accept) {
+        s.phi[i] = phi_p; s.alo[i] = lo_p; s.ahi[i] = hi_p;
+        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+          const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
+          s.llb[b] = s.llb_p[b];
+        }
+        s.ll = ll_p; s.lp = lp_p;
+        s.logbw[i] += (1.0 - target) * gain;  // Robbins-Monro, log scale (Particle.h:153)
+        s.acc++;
+      } else {
+        s.theta[i] = th_cur;
+        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+          const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
+          s.llb_p[b] = s.llb[b];
+        }
+        s.logbw[i] -= target * gain;  // Particle.h:165
+      }
+      s.bwi[i]++;
+    }
+
+    // ================= store (before coupling, main.cpp:165-173) =================
+    if (active) {
+      if (a.store_pt) {
+        a.ring_ll[(long long)it * P + p] = s.ll;
+        a.ring_lp[(long long)it * P + p] = s.lp;
+      } else if (r == R - 1) {
+        a.ring_ll[(long long)it * a.chains + chain] = s.ll;
+        a.ring_lp[(long long)it * a.chains + chain] = s.lp;
+      }
+      if (a.save_hot_draws) {
+#pragma unroll UD
+        for (int i = 0; i < D; ++i) a.ring_theta[((long long)it * D + i) * P + p] = s.theta[i];
+      } else if (r == R - 1) {
+#pragma unroll UD
+        for (int i = 0; i < D; ++i) a.ring_theta[((long long)it * D + i) * a.chains + chain] = s.theta[i];
+      }
+    }
+
+    // ================= Metropolis coupling (main.cpp:282-344) =================
+    if (do_couple) {
+      s_x[tid] = s.ll;
+      if (r < R - 1) {
+        double u;
+        if (a.rng_mode) u = rp[3LL * a.d_free * R + r];
+        else {
+          DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, (unsigned)r, 1u | (gchain_hi << 8), k0, k1);
+          u = drj_u32_to_unif(w.x);
+        }
+        s_logu[tid] = log(u);
+      }
+      __syncthreads();
+      if (r == 0 && active) {
+        // sequential pass hot -> cold; the replica that is swapped upwards is carried along
+        int cur_src = 0;
+        double cur_ll = s_x[base];
+        double b1 = a.beta_raised[0];
+        for (int i = 0; i < R - 1; ++i) {
+          const double ll2 = s_x[base + i + 1];
+          const double b2 = a.beta_raised[i + 1];
+          double acceptance;
+          if (b1 == 0.0) acceptance = (cur_ll * b2) - (ll2 * b2);
+          else acceptance = (ll2 * b1 + cur_ll * b2) - (cur_ll * b1 + ll2 * b2);
+          if (s_logu[base + i] < acceptance) {
+            s_src[base + i] = (short)(i + 1);  // rung i receives the replica that sat at rung i+1
+            s_mc[base + i]++;
+          } else {
+            s_src[base + i] = (short)cur_src;
+            cur_src = i + 1;
+            cur_ll = ll2;
+          }
+          b1 = b2;
+        }
+        s_src[base + R - 1] = (short)cur_src;
+      }
+      __syncthreads();
+      const int src = active ? (int)s_src[tid] : r;
+      const int from = base + src;
+      if (__syncthreads_or(src != r)) {
+        // replica-owned state moves: theta, phi, Jacobian logs, loglike_block, loglike, logprior.
+        // rung-owned state stays: beta, bw, bw_index, accept_count (main.cpp:317-336).
+        constexpr int NV = 4 * D + B + 2;
+        constexpr int UX = (D <= 8 && B <= 8) ? 16 : 1;
+#pragma unroll UX
+        for (int v0 = 0; v0 < NV; v0 += DRJ_EXCH) {
+#pragma unroll
+          for (int e = 0; e < DRJ_EXCH; ++e) {
+            const int v = v0 + e;
+            if (v < NV) {
+              double val;
+              if (v < D) val = s.theta[v];
+              else if (v < 2 * D) val = s.phi[v - D];
+              else if (v < 3 * D) val = s.alo[v - 2 * D];
+              else if (v < 4 * D) val = s.ahi[v - 3 * D];
+              else if (v < 4 * D + B) val = s.llb[v - 4 * D];
+              else if (v == 4 * D + B) val = s.ll;
+              else val = s.lp;
+              s_x[e * DRJ_NT + tid] = val;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int e = 0; e < DRJ_EXCH; ++e) {
+            const int v = v0 + e;
+            if (v < NV) {
+              const double val = s_x[e * DRJ_NT + from];
+              if (v < D) s.theta[v] = val;
+              else if (v < 2 * D) s.phi[v - D] = val;
+              else if (v < 3 * D) s.alo[v - 2 * D] = val;
+              else if (v < 4 * D) s.ahi[v - 3 * D] = val;
+              else if (v < 4 * D + B) { s.llb[v - 4 * D] = val; s.llb_p[v - 4 * D] = val; }
+              else if (v == 4 * D + B) s.ll = val;
+              else s.lp = val;
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+
+    // ================= abort on error (Rcpp::stop in the reference) =================
+    // one barrier: own error, or (seen by thread 0) an error reported by any other CTA
+    int stop = err;
+    if (tid == 0 && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
+    if (__syncthreads_or(stop)) break;
+  }
+
+  // ---- write state back
+  if (active) {
+#pragma unroll UD
+    for (int i = 0; i < D; ++i) {
+      const long long o = (long long)i * P + p;
+      a.theta[o] = s.theta[i]; a.phi[o] = s.phi[i]; a.logbw[o] = s.logbw[i];
+      a.adj_lo[o] = s.alo[i]; a.adj_hi[o] = s.ahi[i]; a.bw_index[o] = s.bwi[i];
+    }
+#pragma unroll UB
+    for (int b = 0; b < B; ++b) a.ll_block[(long long)b * P + p] = s.llb[b];
+    a.ll[p] = s.ll; a.lp[p] = s.lp; a.accept[p] = s.acc;
+    if (do_couple && r < R - 1) a.mc_accept[chain * (R - 1) + r] += s_mc[tid];
+  }
+}
+
+// ------------------------------------------------------------------ kernels
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant__ DrjKernelArgs a) {
+  drj_init_body<M>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
+  drj_sweep_body<M>(a);
+}

@@ -172,6 +172,7 @@ static double halfdomain_logprior(const double* p, int d, const ora_list* misc) 
 
 static const ora_model MODELS[] = {
     {"example", example_loglike, example_logprior},
+    {"example_exact", example_loglike, example_logprior},
     {"coupling", coupling_loglike, coupling_logprior},
     {"blocks", blocks_loglike, blocks_logprior},
     {"doublewell", doublewell_loglike, zero_logprior},

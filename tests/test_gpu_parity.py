@@ -1,0 +1,198 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical inputs.
+
+Replay mode: both sides consume the SAME uniform stream in the reference's order;
+gate = BASELINE.json's: log-likelihoods / states within 1e-10 relative, acceptance and coupling
+counts bit-exact.  Philox mode: the oracle implements the same counter layout, so the same gate
+applies to the production RNG path.
+"""
+import numpy as np
+import pytest
+
+from helpers import Case, POPULATION, assert_parity, beta_ladder, run_gpu, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10  # BASELINE.json north_star: "within 1e-10 relative tolerance"
+
+
+def normal_data(n, seed=3, mean=3.0, sd=2.0):
+    return np.random.Generator(np.random.Philox(seed)).normal(mean, sd, n)
+
+
+def multilevel_case(G, chains, rungs, burnin=30, samples=30):
+    rng = np.random.Generator(np.random.Philox(5))
+    mu = rng.normal(0, 1, G)
+    data = [rng.normal(mu[g], 1.0, 5) for g in range(G)]
+    return Case("multilevel", [-5.0] * G, [5.0] * G, data=data, blocks=[[g + 1, G + 1] for g in range(G)],
+                beta=beta_ladder(rungs), chains=chains, burnin=burnin, samples=samples)
+
+
+CASES = {
+    # K1 model (inst/extdata/example_loglike_logprior.cpp), data resident in shared memory
+    "example_n100": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100)], chains=3, burnin=200, samples=200),
+    "example_n100_odd": Case("example", [-10, 0], [10, np.inf], data=[normal_data(101)], chains=2),
+    "example_exact": Case("example_exact", [-10, 0], [10, np.inf], data=[normal_data(100)], chains=3),
+    "example_rungs4": Case("example", [-10, 0], [10, np.inf], data=[normal_data(50)], beta=beta_ladder(4), chains=5,
+                           burnin=100, samples=100),
+    "example_rungs32_hot": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20)], beta=beta_ladder(32, 2.0),
+                                chains=9, save_hot_draws=True),
+    "example_coupling_off": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20)], beta=beta_ladder(3),
+                                 chains=2, coupling_on=False),
+    # data streamed through shared memory in tiles (n > 2 tiles), ragged last tile
+    "example_stream": Case("example", [-10, 0], [10, np.inf], data=[normal_data(10001)], beta=beta_ladder(2), chains=3,
+                           burnin=6, samples=6),
+    # inst/extdata/coupling_loglike_logprior.cpp, 20 rungs (vignettes/metropolis_coupling.Rmd)
+    "coupling_r20": Case("coupling", [-10, 0, -np.inf], [10, 10, np.inf], data=[normal_data(100, 4, 10.0, 1.0)],
+                         beta=beta_ladder(20), chains=3, burnin=60, samples=60),
+    "normal_mu": Case("normal_mu", [-np.inf], [np.inf], data=[normal_data(100)], chains=4),
+    # K2: double well, 20 rungs, alpha = 2, gamma fixed (skip_param)
+    "doublewell_k2": Case("doublewell", [-2, 30], [2, 30], beta=beta_ladder(20, 2.0), chains=7, burnin=100, samples=100),
+    # K3: logistic growth, 10 rungs
+    "logistic_k3": Case("logistic", [1, 1, 50], [100, 2, 200], data=[POPULATION["pop"], POPULATION["time"]],
+                        beta=beta_ladder(10), chains=5, burnin=40, samples=40),
+    # K4 family: multilevel blocks, shipped size (5 groups) and K4 size (50 groups, 51 blocks)
+    "multilevel_g5": multilevel_case(5, 4, 4),
+    "multilevel_g50": multilevel_case(50, 3, 16, burnin=10, samples=10),
+    # all four transform types + a fixed parameter (test-mcmc-with-r-likelihood-and-prior.R:177-221)
+    "returnprior": Case("returnprior", [-np.inf, -np.inf, 0, 0], [np.inf, 0, np.inf, 1], chains=4, burnin=150, samples=150),
+    "testfile": Case("testfile", [-10, 0], [10, np.inf], data=[normal_data(1000)], chains=2),
+    "testfile_nulllike": Case("testfile_nulllike", [-10, 0], [10, np.inf], data=[normal_data(10)], chains=2),
+    # -Inf over half the domain with a beta = 0 rung (test-Inf_checks_work.R:156-243)
+    "halfdomain_like": Case("halfdomain_like", [0], [1], beta=[0.0, 1.0], chains=3, save_hot_draws=True,
+                            init=np.full((3, 1), 0.1), burnin=200, samples=200),
+    "halfdomain_prior": Case("halfdomain_prior", [0], [1], beta=[0.0, 1.0], chains=3, save_hot_draws=True,
+                             init=np.full((3, 1), 0.1), burnin=200, samples=200),
+}
+
+
+def blocks_case():
+    rng = np.random.Generator(np.random.Philox(9))
+    sizes = [10, 12, 14, 11, 12, 12]  # chickwts group sizes (vignettes/blocks.Rmd)
+    data = [rng.normal(250 + 20 * g, 50.0, n) for g, n in enumerate(sizes)]
+    tmin = [0.0] * 6 + [0.0, -np.inf, 0.0]
+    tmax = [np.inf] * 9
+    blocks = [[g + 1, 7] for g in range(6)] + [[1, 2, 3, 4, 5, 6], [7], [7]]
+    init = np.tile(np.array([250.0] * 6 + [50.0, 250.0, 50.0]), (2, 1))
+    return Case("blocks", tmin, tmax, data=data, blocks=blocks, chains=2, init=init, burnin=60, samples=60)
+
+
+CASES["blocks_chickwts"] = blocks_case()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_replay_matches_oracle(name, oracle):
+    case = CASES[name]
+    u = case.replay()
+    ora = run_oracle(oracle, case, "replay", u)
+    gpu = run_gpu(case, "replay", u)
+    assert_parity(gpu, ora, RTOL, what=f"[{name}] ")
+
+
+@pytest.mark.parametrize("name", ["example_n100", "example_rungs4", "doublewell_k2", "logistic_k3", "multilevel_g5",
+                                  "returnprior", "coupling_r20"])
+def test_philox_matches_oracle(name, oracle):
+    case = CASES[name]
+    ora = run_oracle(oracle, case, "philox", seed=1234, chain_offset=5)
+    gpu = run_gpu(case, "philox", seed=1234, chain_offset=5)
+    assert_parity(gpu, ora, RTOL, what=f"[{name}/philox] ")
+
+
+def test_first_row_is_init(oracle):
+    """tests/testthat/test-mcmc-with-r-likelihood-and-prior.R:170-172: iteration 1 == init exactly."""
+    init = np.array([[-5.0, 1.5], [5.0, 0.5]])
+    case = Case("example", [-10, 0], [10, np.inf], data=[normal_data(30)], chains=2, init=init)
+    gpu = run_gpu(case, "philox", seed=3)
+    assert np.array_equal(gpu["theta_burnin"][:, 0, 0, :], init)
+
+
+def test_stream_tma_and_plain_staging_agree():
+    """The TMA bulk-copy pipeline and the plain cooperative staging must give identical bits."""
+    from drjacoby_b200 import _lib
+    case = CASES["example_stream"]
+    a = run_gpu(case, "philox", seed=2)
+    b = run_gpu(case, "philox", seed=2, flags=_lib.FLAG_NO_TMA)
+    for k in a:
+        if k != "t_diff":
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_chunked_launches_are_bitwise_identical():
+    """State round-trips through HBM between launches: any launch split gives the same bits."""
+    case = CASES["example_rungs4"]
+    a = run_gpu(case, "philox", seed=9)
+    b = run_gpu(case, "philox", seed=9, iters_per_launch=7)
+    c = run_gpu(case, "philox", seed=9, chains_per_cta=1)
+    for k in a:
+        if k != "t_diff":
+            assert np.array_equal(a[k], b[k]), k
+            assert np.array_equal(a[k], c[k]), k
+
+
+def test_sharding_invariance():
+    """Chains shard across GPUs by contiguous ranges; the Philox counter carries the GLOBAL chain id,
+    so a shard reproduces its slice of the unsharded run bit for bit."""
+    case = CASES["doublewell_k2"]
+    full = run_gpu(case, "philox", seed=21, chain_offset=100)
+    lo, hi = 3, 7
+    shard = Case(case.model, case.tmin, case.tmax, beta=case.beta, chains=hi - lo, burnin=case.burnin,
+                 samples=case.samples, init=case.init[lo:hi])
+    part = run_gpu(shard, "philox", seed=21, chain_offset=100 + lo)
+    for k in part:
+        if k != "t_diff":
+            assert np.array_equal(part[k], full[k][lo:hi]), k
+
+
+def test_session_api_equals_one_shot():
+    import drjacoby_b200 as drj
+    from helpers import gpu_spec
+    case = CASES["example_rungs4"]
+    one = run_gpu(case, "philox", seed=5)
+    s = drj.Session(drj.Model(builtin=case.model), gpu_spec(case, "philox", seed=5))
+    ms = 0.0
+    for n in (1, 13, 50, 1000):
+        ms += s.advance(n)
+    assert s.iterations_done() == case.burnin + case.samples
+    out = s.download()
+    sweeps, aux = s.launches()
+    s.close()
+    assert sweeps >= 4 and ms > 0
+    for k in one:
+        if k != "t_diff":
+            assert np.array_equal(one[k], out[k]), k
+
+
+@pytest.mark.parametrize("ll,lp,code", [(np.inf, 0.0, 2), (np.nan, 0.0, 2), (0.0, np.inf, 3), (0.0, np.nan, 3)])
+def test_bad_values_abort(ll, lp, code, oracle):
+    """tests/testthat/test-Inf_checks_work.R:2-94: Inf / NA / NaN from the likelihood or prior is an error."""
+    import drjacoby_b200 as drj
+    case = Case("const", [-10], [10], misc=[[ll], [lp]], chains=2, init=np.ones((2, 1)))
+    with pytest.raises(drj.DrjacobyError) as e:
+        run_gpu(case, "philox")
+    assert e.value.code == code
+    assert ("likelihood" if code == 2 else "prior") in str(e.value)
+    with pytest.raises(oracle.OracleError) as eo:
+        run_oracle(oracle, case, "philox")
+    assert eo.value.code == code
+
+
+def test_neg_inf_at_init_aborts(oracle):
+    """tests/testthat/test-Inf_checks_work.R:97-153"""
+    import drjacoby_b200 as drj
+    for model in ("halfdomain_like", "halfdomain_prior"):
+        case = Case(model, [0], [1], chains=2, init=np.array([[0.2], [0.9]]))
+        with pytest.raises(drj.DrjacobyError) as e:
+            run_gpu(case, "philox")
+        assert e.value.code == 1 and e.value.chain == 1 and "Starting values" in str(e.value)
+
+
+def test_halfdomain_semantics():
+    """test-Inf_checks_work.R:183-243: the beta = 0 rung roams into the -Inf half, the cold rung never does."""
+    case = CASES["halfdomain_like"]
+    out = run_gpu(case, "philox", seed=1)
+    th = np.concatenate([out["theta_burnin"], out["theta_sampling"]], axis=2)[..., 0]  # [chains, rungs, iters]
+    ll = np.concatenate([out["loglike_burnin"], out["loglike_sampling"]], axis=2)
+    assert (th[:, 0].max(axis=1) > 0.5).all() and (th[:, 1].max(axis=1) <= 0.5).all()
+    assert np.all(np.isneginf(ll[:, 0][th[:, 0] > 0.5])) and np.all(np.isfinite(ll[:, 0][th[:, 0] < 0.5]))
+    out2 = run_gpu(CASES["halfdomain_prior"], "philox", seed=1)
+    th2 = np.concatenate([out2["theta_burnin"], out2["theta_sampling"]], axis=2)[..., 0]
+    assert (th2 <= 0.5).all()
