@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the drjacoby_b200 sampling core.
+
+Workload (BASELINE.json configs[4], "K5"): normal model (mu, sigma) on n = 1e7 synthetic data
+points, 1e5 chains x 32 rungs sharded over 8 GPUs = 12,500 chains x 32 rungs per GPU (weak scaling:
+per-GPU work is fixed).  A "step" is ONE MCMC iteration of the hot path over all chain-rungs of the
+shard: every rung updates both parameters (2 data sweeps of n points per chain-rung), samples are
+stored, Metropolis coupling runs.  Metric: parameter updates per second (chains x rungs x free
+parameters x iterations / time), whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                # our arm
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # CPU arm (oracle port)
+
+Lines: ONE JSON object on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "param_updates_per_sec"
+UNIT = "param-updates/s"
+N_DATA = 10_000_000
+CHAINS_PER_GPU = 12_500
+RUNGS = 32
+D_FREE = 2
+FLOP_PER_DATUM = 4.0  # sub, mul, fma(=2) per datum of the normal log-density
+
+
+def synth_data(n=N_DATA):
+    return np.random.Generator(np.random.Philox(1)).normal(3.0, 2.0, n)
+
+
+def default_init(chains, seed):
+    """R/main.R:299-314 for mu in [-10,10] (type 3) and sigma in [0,Inf) (type 2)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    p1, p2 = rng.random(chains), rng.random(chains)
+    return np.stack([-10.0 + 20.0 * p1, 0.0 - np.log(p2)], axis=1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def k5_spec(drj, x, chains, chain_offset, device, burnin, samples, seed=1):
+    return drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=default_init(chains, 1000 + chain_offset),
+                       burnin=burnin, samples=samples, beta_raised=np.linspace(0.0, 1.0, RUNGS),
+                       coupling_on=True, save_hot_draws=False, store_pt=True, rng_mode="philox", seed=seed,
+                       chain_offset=chain_offset, device=device, data=[x], iters_per_launch=1)
+
+
+CPU_RUNGS = 8
+
+
+def cpu_baseline(x, cores, iters=2):
+    """CPU oracle (a port of the reference's loop; the Rcpp reference itself cannot be built here: no R)
+    on `cores` threads.  Bounded sample of the K5 workload: `cores` chains x CPU_RUNGS rungs x `iters`
+    iterations on the full data.  The cost of a parameter update is one likelihood evaluation over the n
+    data points whatever the number of rungs, so fewer rungs shrink the sample, not the per-update cost.
+    The 2 initial evaluations per rung (Particle::init_like) are counted as work, so that the rate is
+    likelihood evaluations/s == parameter updates/s of a long run."""
+    from oracle import pyoracle as po
+    po.build()
+    chains = cores
+    t0 = time.perf_counter()
+    po.run("example", [x], [], np.array([-10.0, 0.0]), np.array([10.0, np.inf]), default_init(chains, 1000),
+           burnin=1, samples=iters, beta_raised=np.linspace(0.0, 1.0, CPU_RUNGS), rng_mode="philox", seed=1,
+           n_threads=cores)
+    dt = time.perf_counter() - t0
+    evals = chains * CPU_RUNGS * D_FREE * (iters + 1)
+    return {"value": evals / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{chains} chains x {CPU_RUNGS} rungs x {iters} iteration(s) + initial likelihood, n={x.size}: "
+                      f"{evals} likelihood evaluations in {dt:.1f} s"}, dt
+
+
+def small_n_sweep(drj, device, chain_offset):
+    """Same model, n = 100 (the K1 data size) over the same 12,500 x 32 chain-rungs: the regime the
+    north_star's 1e10 param-updates/s/box target is evaluated on (SURVEY 8(d) sanity arithmetic)."""
+    x = synth_data(100)
+    spec = drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=default_init(CHAINS_PER_GPU, 77 + chain_offset),
+                       burnin=1, samples=600, beta_raised=np.linspace(0.0, 1.0, RUNGS), store_pt=False, rng_mode="philox",
+                       seed=2, chain_offset=chain_offset, device=device, data=[x], iters_per_launch=100)
+    s = drj.Session(drj.Model(builtin="example"), spec)
+    s.advance(100)
+    ms = s.advance(500)
+    s.close()
+    return {"workload": "normal model n=100, 12500 chains x 32 rungs per GPU", "iterations": 500, "kernel_ms": ms,
+            "value": CHAINS_PER_GPU * RUNGS * D_FREE * 500 / (ms * 1e-3), "unit": UNIT}
+
+
+def ess_sweep(drj, device):
+    """ESS/s (coda definition, min over parameters, summed over chains) on the K1 model: n=100, 1 rung,
+    burnin 1e3 + samples 1e4, 1024 chains; ESS is evaluated on 64 chains and scaled."""
+    from drjacoby_b200 import diagnostics as dg
+    x = synth_data(100)
+    chains = 1024
+    spec = drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=default_init(chains, 5),
+                       burnin=1000, samples=10000, rng_mode="philox", seed=3, device=device, data=[x])
+    t0 = time.perf_counter()
+    out = drj.run_raw(drj.Model(builtin="example"), spec)
+    dt = time.perf_counter() - t0
+    th = out["theta_sampling"][:, 0]  # [chains, samples, d]
+    pick = np.linspace(0, chains - 1, 64).astype(int)
+    ess = np.array([[dg.ess(th[c, :, k]) for k in range(2)] for c in pick]).min(axis=1)
+    return {"workload": "K1 model n=100, 1024 chains x 1 rung, 1e3+1e4 iterations", "wall_s": dt,
+            "ess_per_chain_min_param": float(ess.mean()), "value": float(ess.mean() * chains / dt), "unit": "ESS/s"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import drjacoby_b200 as drj
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    device = local
+    torch.cuda.set_device(device)
+    K, W = args.steps, args.warmup
+    chains = args.chains_per_gpu
+    chain_offset = rank * chains
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # inputs in pinned host memory (the e2e leg copies them every step)
+    x_pin = torch.empty(args.n_data, dtype=torch.float64).pin_memory()
+    x = x_pin.numpy()
+    x[:] = synth_data(args.n_data)
+
+    model = drj.Model(builtin="example")
+    sess = drj.Session(model, k5_spec(drj, x, chains, chain_offset, device, burnin=1, samples=W + K))
+    fp64_peak = drj.fp64_peak_tflops(device)
+
+    for _ in range(W):
+        sess.advance(1)
+    l0 = sess.launches()
+    sw0, st0 = sess.timing()
+    clocks = ClockSampler(device)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        sess.advance(1)  # one launch of the sweep kernel = one iteration over every chain-rung (+ output transposes)
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop() if rank == 0 else None
+    l1 = sess.launches()
+    sw1, st1 = sess.timing()
+    dev_s = (st1 - st0) * 1e-3      # CUDA events on the session stream: sweep kernels + transposes
+    sweep_s = (sw1 - sw0) * 1e-3    # sweep kernels only
+    if world > 1:
+        t = torch.tensor([dev_s, sweep_s, wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, sweep_s, wall = [float(v) for v in t.tolist()]
+    out = sess.download()
+    sess.close()
+    updates_per_gpu = chains * RUNGS * D_FREE * K
+    value = n_gpus * updates_per_gpu / dev_s
+
+    # ---- end to end through the C ABI with host buffers: H2D of the data and inits, init, E2E_IT
+    # iterations, D2H of every output, inside the timed region
+    E2E_IT = args.e2e_iters
+    e2e_calls = max(1, args.e2e_calls)
+    spec_e = k5_spec(drj, x, chains, chain_offset, device, burnin=1, samples=E2E_IT, seed=4)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        out_e = drj.run_raw(model, spec_e)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_wall = float(t.item())
+    e2e_value = n_gpus * chains * RUNGS * D_FREE * E2E_IT * e2e_calls / e2e_wall
+    h2d = x.nbytes + spec_e.theta_init.nbytes + 8 * (2 * 2 + RUNGS)
+    d2h = sum(v.nbytes for v in out_e.values())
+
+    # ---- diagnostics gathered over NCCL at the end (the only collective; not on the hot path)
+    cold_mu = out["theta_sampling"][:, 0, -1, 0]
+    summ = torch.tensor([cold_mu.sum(), float(cold_mu.size), float(out["accept_sampling"][:, -1].sum())],
+                        device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(summ)
+    extra = {}
+    if rank == 0 and not args.no_sweeps:
+        extra["small_n"] = small_n_sweep(drj, device, chain_offset)
+        extra["ess"] = ess_sweep(drj, device)
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        cpu, _ = cpu_baseline(x if args.n_data <= N_DATA else x[:N_DATA], cores, iters=args.cpu_iters)
+
+    if rank == 0:
+        flops_per_launch = FLOP_PER_DATUM * args.n_data * chains * RUNGS * D_FREE  # one launch = one iteration
+        launch_s = sweep_s / K
+        achieved = flops_per_launch / launch_s / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        n_cta = -(-chains // (256 // RUNGS))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"K5 shard: normal model (mu,sigma), n={args.n_data} data points, {chains} chains x {RUNGS} rungs per GPU "
+                                   f"(BASELINE configs[4] = 1e5 chains x 32 rungs over 8 GPUs), Metropolis coupling on, Philox RNG",
+                       "chains_per_gpu": chains, "rungs": RUNGS, "n_data": args.n_data, "free_params": D_FREE,
+                       "step": "one MCMC iteration over all chain-rungs", "l2": f"inputs larger than L2 per sweep: data {x.nbytes/1e6:.0f} MB re-streamed by every CTA",
+                       "parallelism": f"chains sharded over {n_gpus} GPU(s), no hot-path collective"},
+            "timing": {"device_s": dev_s, "sweep_kernel_s": sweep_s, "wall_s": wall, "how": "CUDA events on the session stream, max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "what": f"drj_run_mcmc C-ABI call, host buffers (pinned data), {E2E_IT} iterations per call, {e2e_calls} call(s), includes the initial likelihood sweep"},
+            "gpu_launches": int((l1[0] - l0[0]) + (l1[1] - l0[1])),
+            "launches": {"sweep": int(l1[0] - l0[0]), "transpose": int(l1[1] - l0[1])},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": None, "kernel": "drj_sweep_kernel<DrjModelExample>",
+                         "peak_source": "FP64 FMA probe (drj_fp64_peak_tflops) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
+                         "algorithmic_flop_per_launch": flops_per_launch, "launch_ms": launch_s * 1e3,
+                         "hbm": {"algorithmic_bytes_per_launch": 8.0 * args.n_data * D_FREE * n_cta, "peak_gbs": hbm_peak,
+                                 "achieved_gbs": 8.0 * args.n_data * D_FREE * n_cta / launch_s / 1e9,
+                                 "note": "every CTA streams the data once per sweep (served by L2 after the first reader); far below the HBM roof: FP64-bound"}},
+            "cpu_baseline": cpu,
+            "clocks": clk,
+            "diag": {"mean_cold_mu_last": float(summ[0] / summ[1]), "cold_accepts": int(summ[2])},
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference arm: the reference's CPU algorithm (oracle port; the Rcpp package itself cannot be
+    built or run in this image: no R) on all host cores, bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    x = synth_data(args.n_data)
+    vals, samples = [], []
+    from oracle import pyoracle as po
+    po.build()
+    total = args.warmup + args.steps
+    budget_s = 150.0
+    t_start = time.perf_counter()
+    for i in range(total):
+        b, dt = cpu_baseline(x, cores, iters=1)
+        if i >= args.warmup:
+            vals.append(b["value"])
+            samples.append(b["sample"])
+        if time.perf_counter() - t_start > budget_s and vals:
+            break
+    v = float(np.mean(vals))
+    steps_done = len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+            "warmup": args.warmup, "ms_per_step": 1e3 * cores * RUNGS * D_FREE / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"K5 bounded sample: normal model n={args.n_data}, {cores} chains x {CPU_RUNGS} rungs, 1 iteration per step "
+                                   "(+ the initial likelihood evaluations, counted as work)", "rungs": CPU_RUNGS, "n_data": args.n_data},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": samples[-1]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-data", type=int, default=N_DATA)
+    ap.add_argument("--chains-per-gpu", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--e2e-iters", type=int, default=4)
+    ap.add_argument("--e2e-calls", type=int, default=1)
+    ap.add_argument("--cpu-iters", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sweeps", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -88,6 +88,7 @@ SYMBOLS = {
     "drj_session_iterations_done": (C.c_int, [C.c_void_p]),
     "drj_session_download": (C.c_int, [C.c_void_p, C.POINTER(DrjOutput), C.POINTER(DrjError)]),
     "drj_session_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "drj_session_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "drj_session_destroy": (None, [C.c_void_p]),
     "drj_fp64_peak_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(DrjError)]),
 }

@@ -290,7 +290,7 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init(const __grid_constant__ DrjKernelArgs a) {\n"
        "  drj_init_body<DRJ_USER_MODEL>(a);\n"
        "}\n"
-       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
        "  drj_sweep_body<DRJ_USER_MODEL>(a);\n"
        "}\n";
   return s;
@@ -427,7 +427,8 @@ struct drj_session {
   drj_config cfg;
   const drj_model* model = nullptr;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  double sweep_ms_total = 0.0, stream_ms_total = 0.0;  // CUDA-event time: sweep kernels / sweep + transposes
   DrjKernelArgs a;
   std::vector<void*> allocs;
   int D = 0, B = 0, R = 0, C = 0;
@@ -618,6 +619,7 @@ extern "C" void drj_session_destroy(drj_session* s) {
   for (void* p : s->allocs) cudaFree(p);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev2) cudaEventDestroy(s->ev2);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -636,6 +638,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
+  CUDA_TRY(cudaEventCreate(&s->ev2));
   if (model->jit && !load_driver_api()) return set_err(err, DRJ_ERR_CUDA, "CUDA driver entry points unavailable");
 
   // ---- launch geometry: all rungs of a chain in one CTA, as many chains per CTA as fit in DRJ_NT
@@ -644,11 +647,16 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
   const int max_cpc = std::max(1, DRJ_NT / R);
   int cpc = cfg->chains_per_cta > 0 ? std::min(cfg->chains_per_cta, max_cpc) : max_cpc;
-  if (cfg->chains_per_cta <= 0 && !(model->datum_form)) {
-    // generic models do not share data tiles: prefer more, smaller CTAs when chains are few
+  if (cfg->chains_per_cta <= 0) {
+    // ~128-thread CTAs: with ~128 registers per thread four of them fill an SM's register file, and
+    // a finer CTA grain shortens the last, partially filled wave (all CTAs do equal work, so the
+    // tail is a whole-CTA quantum).  Fewer chains per CTA still when there are few chains, so that
+    // every SM gets work.
+    cpc = std::min(cpc, std::max(1, 128 / R));
     const long long want_ctas = 4LL * prop.multiProcessorCount;
     const int fit = (int)std::max<long long>(1, (C + want_ctas - 1) / want_ctas);
     cpc = std::min(cpc, fit);
+    cpc = std::max(cpc, std::min(max_cpc, (32 + R - 1) / R));  // but never less than one full warp
   }
   s->cpc = cpc;
   s->nthreads = std::min(DRJ_NT, ((cpc * R + 31) / 32) * 32);
@@ -782,11 +790,15 @@ extern "C" int drj_session_advance(drj_session* s, int n_iter, float* kernel_ms,
     // burn-in row index = update index (row 0 = initial values); sampling column = t - burnin
     const int col0 = sampling ? (s->t_done - nb) : (s->t_done + 1);
     if ((rc = flush_ring(s, nt, sampling, col0, err))) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
-    if (kernel_ms) {
-      float ms = 0.f;
+    {
+      float ms = 0.f, ms2 = 0.f;
       CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
-      *kernel_ms += ms;
+      CUDA_TRY(cudaEventElapsedTime(&ms2, s->ev0, s->ev2));
+      if (kernel_ms) *kernel_ms += ms;
+      s->sweep_ms_total += ms;
+      s->stream_ms_total += ms2;
     }
     if ((rc = check_device_error(s, s->t_done + 1, err))) return rc;
     s->t_done += nt;
@@ -806,6 +818,13 @@ extern "C" int drj_session_launches(const drj_session* s, int64_t* sweep_launche
   if (!s) return DRJ_ERR_ARG;
   if (sweep_launches) *sweep_launches = s->sweep_launches;
   if (aux_launches) *aux_launches = s->aux_launches;
+  return DRJ_OK;
+}
+
+extern "C" int drj_session_timing(const drj_session* s, double* sweep_ms_total, double* stream_ms_total) {
+  if (!s) return DRJ_ERR_ARG;
+  if (sweep_ms_total) *sweep_ms_total = s->sweep_ms_total;
+  if (stream_ms_total) *stream_ms_total = s->stream_ms_total;
   return DRJ_OK;
 }
 

@@ -143,18 +143,28 @@ struct DrjTiles {  // no tiles for generic models
   __device__ __forceinline__ void init(const DrjKernelArgs&) {}
 };
 
+// The tile buffers and their mbarriers are static shared memory owned by these two accessors, so
+// that every user (kernel body, the noinline sweep routine) sees a pointer the compiler KNOWS is
+// shared memory (a pointer carried through a struct degrades to generic LD.E loads).
+template <class M>
+__device__ __forceinline__ double* drj_tile_buf() {
+  __shared__ __align__(128) double s_buf[2 * DRJ_TILE + 8];  // + slack for the pipelined prefetch
+  return s_buf;
+}
+template <class M>
+__device__ __forceinline__ unsigned long long* drj_tile_bars() {
+  __shared__ __align__(8) unsigned long long s_full[2];
+  return s_full;
+}
+
 template <class M>
 struct DrjTiles<M, true> {
-  double* buf;                 // [2][DRJ_TILE]
-  unsigned long long* full;    // [2] mbarriers
   unsigned ph0, ph1;           // phase parity of each stage
-  bool resident;               // whole item lives in buf for the life of the kernel
+  bool resident;               // whole item lives in the tile buffer for the life of the kernel
   bool tma;
   __device__ __forceinline__ void init(const DrjKernelArgs& a) {
-    __shared__ __align__(128) double s_buf[2 * DRJ_TILE];
-    __shared__ __align__(8) unsigned long long s_full[2];
-    buf = s_buf;
-    full = s_full;
+    double* s_buf = drj_tile_buf<M>();
+    unsigned long long* full = drj_tile_bars<M>();
     ph0 = ph1 = 0;
     tma = a.use_tma != 0;
     // single-item models keep the data resident when it fits the two tiles
@@ -174,59 +184,97 @@ struct DrjTiles<M, true> {
   }
 };
 
-// CTA-wide likelihood sweep: every thread evaluates ITS OWN theta against the SAME data item.
-// Must be called by all threads of the CTA (uniform control flow).  Each thread's sum runs in
-// index order (the reference's `ret +=` loop, inst/extdata/example_loglike_logprior.cpp:15-18).
-template <class M>
-__device__ __forceinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typename M::Consts& k,
-                                                 const double* __restrict__ g, long long n) {
-  double acc = 0.0;
-  if (T.resident) {
-    const double2* t2 = reinterpret_cast<const double2*>(T.buf);
-    const int n2 = (int)(n >> 1);
-#pragma unroll 8
-    for (int j = 0; j < n2; ++j) {
-      double2 v = t2[j];
-      acc = M::datum(k, v.x, acc);
-      acc = M::datum(k, v.y, acc);
+// DRJ_NACC interleaved partial sums: datum j -> accumulator (j mod 8), combined pairwise at the end.
+// One dependent DFMA chain per thread cannot keep the FP64 pipe busy (profiles/README.md, round 1:
+// 67 % pipe utilisation, "wait" stalls on the accumulate DFMA); tools/fp64_pattern_probe.cu shows the
+// pipe needs >= 4-8 independent chains per thread at 16 warps/SM.  The assignment is by GLOBAL datum
+// index (tiles start at multiples of 8), so the result does not depend on tile size or launch
+// geometry.  It is a reassociation of the reference's sequential `ret +=` loop
+// (inst/extdata/example_loglike_logprior.cpp:15-18): same terms, error O(ulp), inside the 1e-10 gate.
+#define DRJ_NACC 8
+struct DrjAcc {
+  double a[DRJ_NACC];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int q = 0; q < DRJ_NACC; ++q) a[q] = 0.0;
+  }
+  __device__ __forceinline__ double total() const {
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
+};
+
+// FULL = the span is a whole tile: compile-time trip count, which lets ptxas keep the loads of the
+// next group(s) far ahead of their use (the same source with a run-time count is scheduled with the
+// LDS only ~20 cycles ahead and stalls on it, profiles/README.md).
+template <class M, bool FULL>
+__device__ __forceinline__ void drj_accum_span(const typename M::Consts& k, const double* __restrict__ buf, int cnt,
+                                               DrjAcc& A) {
+  const double2* t2 = reinterpret_cast<const double2*>(buf);
+  const int n8 = FULL ? (DRJ_TILE / 8) : (cnt >> 3);
+  if (n8 > 0) {
+    // software pipeline: the broadcast LDS.128s of group j+1 are in flight while group j is in the
+    // FP64 pipe (tools/fp64_pattern_probe2.cu).  The last trip prefetches 8 doubles past the span;
+    // the tile buffer carries 8 doubles of slack.
+    double2 c0 = t2[0], c1 = t2[1], c2 = t2[2], c3 = t2[3];
+#pragma unroll 2
+    for (int j = 0; j < n8; ++j) {
+      const double2 n0 = t2[4 * j + 4], n1 = t2[4 * j + 5], n2 = t2[4 * j + 6], n3 = t2[4 * j + 7];
+      A.a[0] = M::datum(k, c0.x, A.a[0]);
+      A.a[1] = M::datum(k, c0.y, A.a[1]);
+      A.a[2] = M::datum(k, c1.x, A.a[2]);
+      A.a[3] = M::datum(k, c1.y, A.a[3]);
+      A.a[4] = M::datum(k, c2.x, A.a[4]);
+      A.a[5] = M::datum(k, c2.y, A.a[5]);
+      A.a[6] = M::datum(k, c3.x, A.a[6]);
+      A.a[7] = M::datum(k, c3.y, A.a[7]);
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     }
-    if (n & 1) acc = M::datum(k, T.buf[n - 1], acc);
-    return acc;
+  }
+  if (!FULL) {
+    const int j0 = n8 << 3;
+#pragma unroll
+    for (int q = 0; q < DRJ_NACC - 1; ++q)
+      if (j0 + q < cnt) A.a[q] = M::datum(k, buf[j0 + q], A.a[q]);
+  }
+}
+
+// CTA-wide likelihood sweep: every thread evaluates ITS OWN theta against the SAME data item.
+// Must be called by all threads of the CTA (uniform control flow).
+template <class M>
+__device__ __noinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typename M::Consts& k,
+                                                 const double* __restrict__ g, long long n) {
+  double* const buf = drj_tile_buf<M>();
+  unsigned long long* const full = drj_tile_bars<M>();
+  DrjAcc A;
+  A.zero();
+  if (T.resident) {
+    drj_accum_span<M, false>(k, buf, (int)n, A);
+    return A.total();
   }
   const long long ntiles = (n + DRJ_TILE - 1) / DRJ_TILE;
   const unsigned tile_bytes = DRJ_TILE * sizeof(double);
   if (T.tma) {
     // prologue: TMA engine fills both stages (the buffer is padded to whole tiles by the host)
     if (threadIdx.x == 0) {
-      drj_mbar_expect_tx(&T.full[0], tile_bytes);
-      drj_bulk_g2s(T.buf, g, tile_bytes, &T.full[0]);
+      drj_mbar_expect_tx(&full[0], tile_bytes);
+      drj_bulk_g2s(buf, g, tile_bytes, &full[0]);
       if (ntiles > 1) {
-        drj_mbar_expect_tx(&T.full[1], tile_bytes);
-        drj_bulk_g2s(T.buf + DRJ_TILE, g + DRJ_TILE, tile_bytes, &T.full[1]);
+        drj_mbar_expect_tx(&full[1], tile_bytes);
+        drj_bulk_g2s(buf + DRJ_TILE, g + DRJ_TILE, tile_bytes, &full[1]);
       }
     }
     for (long long kt = 0; kt < ntiles; ++kt) {
       const int s = (int)(kt & 1);
-      if (s == 0) { drj_mbar_wait(&T.full[0], T.ph0); T.ph0 ^= 1u; }
-      else        { drj_mbar_wait(&T.full[1], T.ph1); T.ph1 ^= 1u; }
+      if (s == 0) { drj_mbar_wait(&full[0], T.ph0); T.ph0 ^= 1u; }
+      else        { drj_mbar_wait(&full[1], T.ph1); T.ph1 ^= 1u; }
       const long long rem = n - kt * DRJ_TILE;
       const int cnt = rem < DRJ_TILE ? (int)rem : DRJ_TILE;
-      const double2* t2 = reinterpret_cast<const double2*>(T.buf + s * DRJ_TILE);
-      if (cnt == DRJ_TILE) {
-#pragma unroll 8
-        for (int j = 0; j < DRJ_TILE / 2; ++j) {
-          double2 v = t2[j];
-          acc = M::datum(k, v.x, acc);
-          acc = M::datum(k, v.y, acc);
-        }
-      } else {
-        const double* t1 = T.buf + s * DRJ_TILE;
-        for (int j = 0; j < cnt; ++j) acc = M::datum(k, t1[j], acc);
-      }
+      if (cnt == DRJ_TILE) drj_accum_span<M, true>(k, buf + s * DRJ_TILE, cnt, A);
+      else drj_accum_span<M, false>(k, buf + s * DRJ_TILE, cnt, A);
       __syncthreads();  // everyone is done with stage s before the engine refills it
       if (threadIdx.x == 0 && kt + 2 < ntiles) {
-        drj_mbar_expect_tx(&T.full[s], tile_bytes);
-        drj_bulk_g2s(T.buf + s * DRJ_TILE, g + (kt + 2) * DRJ_TILE, tile_bytes, &T.full[s]);
+        drj_mbar_expect_tx(&full[s], tile_bytes);
+        drj_bulk_g2s(buf + s * DRJ_TILE, g + (kt + 2) * DRJ_TILE, tile_bytes, &full[s]);
       }
     }
   } else {
@@ -235,12 +283,12 @@ __device__ __forceinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typ
       const long long rem = n - kt * DRJ_TILE;
       const int cnt = rem < DRJ_TILE ? (int)rem : DRJ_TILE;
       __syncthreads();
-      for (int j = threadIdx.x; j < cnt; j += blockDim.x) T.buf[j] = g[kt * DRJ_TILE + j];
+      for (int j = threadIdx.x; j < cnt; j += blockDim.x) buf[j] = g[kt * DRJ_TILE + j];
       __syncthreads();
-      for (int j = 0; j < cnt; ++j) acc = M::datum(k, T.buf[j], acc);
+      drj_accum_span<M, false>(k, buf, cnt, A);
     }
   }
-  return acc;
+  return A.total();
 }
 
 template <class M>
@@ -325,9 +373,15 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
 #pragma unroll UB
   for (int b = 0; b < B; ++b) s.llb[b] = 0.0;
   // init_like: every block listed by every parameter (duplicates re-evaluated), Particle.h:62-68
+  // (a block listed by several parameters is evaluated once: same theta, same value)
+  unsigned long long seen = 0ULL;
   for (int i = 0; i < D; ++i)
     for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
       const int b = a.block_idx[j];
+      if (b <= 64) {
+        if ((seen >> (b - 1)) & 1ULL) continue;
+        seen |= 1ULL << (b - 1);
+      }
       s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
     }
   s.ll = 0.0;
@@ -615,6 +669,6 @@ __global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant_
   drj_init_body<M>(a);
 }
 template <class M>
-__global__ void __launch_bounds__(DRJ_NT) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
+__global__ void __launch_bounds__(DRJ_NT, 2) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
   drj_sweep_body<M>(a);
 }

@@ -222,6 +222,12 @@ class Session:
         L.lib().drj_session_launches(self._h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
 
+    def timing(self) -> tuple[float, float]:
+        """Cumulative CUDA-event ms on the session stream: (sweep kernels, sweep kernels + transposes)."""
+        a, b = C.c_double(0), C.c_double(0)
+        L.lib().drj_session_timing(self._h, C.byref(a), C.byref(b))
+        return float(a.value), float(b.value)
+
     def download(self) -> dict:
         out = self.spec.alloc_outputs()
         cout = _c_output(out)

@@ -173,6 +173,8 @@ int drj_session_advance(drj_session* s, int n_iter, float* kernel_ms, drj_error*
 int drj_session_iterations_done(const drj_session* s); /* rows stored so far, incl. the initial row */
 int drj_session_download(drj_session* s, drj_output* out, drj_error* err);
 int drj_session_launches(const drj_session* s, int64_t* sweep_launches, int64_t* aux_launches);
+/* cumulative CUDA-event time on the session's stream: sweep kernels only / sweep kernels + output transposes */
+int drj_session_timing(const drj_session* s, double* sweep_ms_total, double* stream_ms_total);
 void drj_session_destroy(drj_session* s);
 
 /* ---- measurement helper: FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA), the
