@@ -1,0 +1,233 @@
+"""The public run_mcmc() path on the GPU: the reference's own published numbers reproduced by the CUDA
+sampler (R-compatible replay stream), user models compiled with NVRTC, and the statistical checks of
+the reference's test-suite / "checks" vignettes in normal (Philox) mode."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import drjacoby_b200 as drj
+from drjacoby_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vignettes.json")))
+
+NORMAL_SRC = r"""
+// inst/extdata/example_loglike_logprior.cpp rewritten against cuda_template.cu
+__device__ double loglike(const double* params, const DrjList& data, const DrjList& misc, int block) {
+  double mu = params[P_mu];
+  double sigma = params[P_sigma];
+  const double* x = data.item(DATA_x);
+  double ret = 0.0;
+  for (long long i = 0; i < data.len(DATA_x); ++i) ret += R::dnorm(x[i], mu, sigma, true);
+  return ret;
+}
+__device__ double logprior(const double* params, const DrjList& misc) {
+  return -log(20.0) + R::dlnorm(params[P_sigma], 0.0, 1.0, true);
+}
+"""
+
+
+def vignette_setup():
+    rs = drj.RStream(1)
+    data = {"x": rs.rnorm(10, 3, 2)}
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+    return rs, data, df
+
+
+def rates_of(res, burnin, samples, d):
+    return [[api._printed_rate(res.raw["accept_burnin"][c, -1], burnin, d), api._printed_rate(res.raw["accept_sampling"][c, -1], samples, d)]
+            for c in range(res.raw["accept_burnin"].shape[0])]
+
+
+@pytest.mark.parametrize("builtin", ["example", "example_exact"])
+def test_example_vignette_on_the_gpu(builtin):
+    """docs/articles/example.html: head(mcmc$output), 20 acceptance rates, Rhat, ESS -- from the GPU."""
+    g = GOLD["example"]
+    rs, data, df = vignette_setup()
+    drj.use_builtin(builtin)
+    kw = dict(data=data, df_params=df, loglike="loglike", logprior="logprior", burnin=1e3, samples=1e3, rng="r", seed=rs, silent=True)
+    res = drj.run_mcmc(**kw)
+    head = res.output.head(6)
+    for row, want in zip(head.itertuples(index=False), g["head_rows_chain1"]["rows"]):
+        for have, w in zip((row.mu, row.sigma, row.logprior, row.loglikelihood), want[1:]):
+            digits = len(repr(w).split(".")[1])
+            assert abs(have - w) <= 0.5000001 * 10.0 ** (-digits), (row, want)
+    assert rates_of(res, 1000, 1000, 2) == g["acceptance_pct_run1"]
+    assert [float(res.diagnostics["rhat"][k]) for k in ("mu", "sigma")] == g["rhat"]
+    np.testing.assert_allclose([res.diagnostics["ess"][k] for k in ("mu", "sigma")], g["ess"], atol=5e-5)
+    res2 = drj.run_mcmc(**kw)  # the vignette's second run continues the stream
+    assert rates_of(res2, 1000, 1000, 2) == g["acceptance_pct_run2"]
+
+
+def test_coupling_vignette_on_the_gpu():
+    """docs/articles/metropolis_coupling.html:284,287: nine 1-rung runs, then 20 rungs: 42.5 % / 44 %."""
+    rs = drj.RStream(1)
+    data = {"x": rs.rnorm(100, 10, 1)}
+    df = drj.define_params("name", "alpha", "min", -10, "max", 10, "init", 5, "name", "beta", "min", 0, "max", 10, "init", 5,
+                           "name", "epsilon", "min", -np.inf, "max", np.inf, "init", 0)
+    drj.use_builtin("coupling")
+    kw = dict(data=data, df_params=df, loglike="loglike", logprior="logprior", burnin=1e3, samples=1e4, chains=1, rng="r",
+              seed=rs, silent=True, as_frames=False)
+    for _ in range(9):
+        drj.run_mcmc(**kw)
+    res = drj.run_mcmc(rungs=20, **kw)
+    assert rates_of(res, 1000, 10000, 3)[0] == GOLD["metropolis_coupling"]["acceptance_pct_all_runs"][:2]
+
+
+def test_double_well_vignette_on_the_gpu():
+    """docs/articles/checks_double_well.html:203,206: 11 rungs, alpha = 2, fixed gamma: 21.7 % / 22 %."""
+    rs = drj.RStream(1)
+    df = drj.define_params("name", "mu", "min", -2, "max", 2, "name", "gamma", "min", 30, "max", 30)
+    drj.use_builtin("doublewell")
+    kw = dict(data={"x": [-1.0]}, df_params=df, loglike="loglike", logprior="logprior", burnin=1e3, samples=1e5, chains=1,
+              rng="r", seed=rs, silent=True, as_frames=False)
+    drj.run_mcmc(rungs=1, **kw)
+    res = drj.run_mcmc(rungs=11, alpha=2, **kw)
+    assert rates_of(res, 1000, 100000, 2)[0] == GOLD["double_well"]["acceptance_pct_all_runs"][:2]
+
+
+def test_nvrtc_user_model_equals_builtin():
+    """A model written against cuda_template.cu, compiled at run time with NVRTC for sm_100a, gives the
+    same bits as the nvcc-compiled built-in with the same arithmetic (example_exact)."""
+    x = np.random.default_rng(2).normal(3, 2, 64)
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+    kw = dict(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=100, samples=200, rungs=4, chains=6,
+              seed=99, silent=True)
+    src = drj.source_cuda(NORMAL_SRC)
+    a = drj.run_mcmc(**kw)
+    drj.use_builtin("example_exact")
+    b = drj.run_mcmc(**kw)
+    for k in a.raw:
+        if k != "t_diff":
+            assert np.array_equal(a.raw[k], b.raw[k]), k
+    assert src.model("loglike", "logprior").compile_seconds() >= 0.0
+
+
+def test_nvrtc_errors_are_reported():
+    df = drj.define_params("name", "mu", "min", -10, "max", 10)
+    drj.source_cuda("__device__ double loglike(const double* p, const DrjList& d, const DrjList& m, int b) { return undefined_symbol; }\n"
+                    "__device__ double logprior(const double* p, const DrjList& m) { return 0.0; }")
+    with pytest.raises(drj.DrjacobyError) as e:
+        drj.run_mcmc({"x": [1.0]}, df, loglike="loglike", logprior="logprior", burnin=10, samples=10, chains=1, silent=True)
+    assert e.value.code == 12 and "undefined_symbol" in str(e.value)
+
+
+def test_nvrtc_block_model_and_misc():
+    """Blocks + misc + several data items through the JIT path: the multilevel model written by hand
+    (inst/extdata/checks/multilevel_loglike_logprior.cpp) against the built-in."""
+    G = 5
+    rng = np.random.default_rng(5)
+    data = {f"g{g + 1}": rng.normal(rng.normal(), 1.0, 5) for g in range(G)}
+    src = r"""
+    __device__ double loglike(const double* params, const DrjList& data, const DrjList& misc, int block) {
+      const int G = (int)misc.scalar(MISC_n_groups);
+      double ret = 0.0;
+      if (block == G + 1) {
+        for (int i = 0; i < G; ++i) ret += R::dnorm(params[i], 0.0, 1.0, true);
+      } else {
+        const double* x = data.item(block - 1);
+        for (long long i = 0; i < data.len(block - 1); ++i) ret += R::dnorm(x[i], params[block - 1], 1.0, true);
+      }
+      return ret;
+    }
+    __device__ double logprior(const double* params, const DrjList& misc) { return 0.0; }
+    """
+    args = []
+    for g in range(G):
+        args += ["name", f"mu_{g + 1}", "min", -5, "max", 5, "block", [g + 1, G + 1]]
+    df = drj.define_params(*args)
+    kw = dict(data=data, df_params=df, loglike="loglike", logprior="logprior", burnin=60, samples=60, rungs=3, chains=4,
+              seed=8, silent=True)
+    drj.source_cuda(src)
+    a = drj.run_mcmc(misc={"n_groups": G}, **kw)
+    drj.use_builtin("multilevel")
+    b = drj.run_mcmc(**kw)
+    for k in a.raw:
+        if k != "t_diff":
+            assert np.array_equal(a.raw[k], b.raw[k]), k
+
+
+def test_multilevel_any_size_specialised_with_nvrtc():
+    """multilevel<G> for a G that is not pre-instantiated is specialised at run time; posterior of
+    vignettes/checks_multilevel_blocks.Rmd: mu_i ~ N(m_i n/(n+1), 1/(n+1))."""
+    G, n = 7, 5
+    rng = np.random.default_rng(6)
+    data = {f"g{g + 1}": rng.normal(rng.normal(), 1.0, n) for g in range(G)}
+    args = []
+    for g in range(G):
+        args += ["name", f"mu_{g + 1}", "min", -5, "max", 5, "block", [g + 1, G + 1]]
+    drj.use_builtin("multilevel")
+    res = drj.run_mcmc(data, drj.define_params(*args), loglike="loglike", logprior="logprior", burnin=500, samples=2000,
+                       chains=64, seed=3, silent=True, as_frames=False)
+    th = res.raw["theta_sampling"][:, 0]  # [chains, samples, G]
+    for g in range(G):
+        m = np.mean(data[f"g{g + 1}"])
+        draws = th[:, :, g].ravel()
+        se = np.sqrt(1.0 / (n + 1) / (res.diagnostics["ess"][f"mu_{g + 1}"]))
+        assert abs(draws.mean() - m * n / (n + 1)) < 6 * se + 1e-3
+        assert abs(draws.var() - 1.0 / (n + 1)) < 0.02
+
+
+def test_normal_posterior_matches_analytic():
+    """vignettes/checks_normal_model.Rmd: posterior of mu is N(mean(x), 1/n); Rhat close to 1."""
+    x = np.random.default_rng(10).normal(1.0, 1.0, 100)
+    df = drj.define_params("name", "mu", "min", -np.inf, "max", np.inf, "init", 0.0)
+    drj.use_builtin("normal_mu")
+    res = drj.run_mcmc({"x": x}, df, loglike="loglike", logprior="logprior", burnin=1000, samples=5000, chains=128, seed=1,
+                       silent=True, as_frames=False)
+    draws = res.raw["theta_sampling"][:, 0, :, 0]
+    ess = res.diagnostics["ess"]["mu"]
+    assert abs(draws.mean() - x.mean()) < 6 * np.sqrt(0.01 / ess) + 1e-4
+    assert abs(draws.var() - 0.01) < 3e-4
+    assert abs(res.diagnostics["rhat"]["mu"] - 1.0) < 0.01
+    # acceptance is tuned to the target by the Robbins-Monro bandwidth adaptation
+    acc = res.raw["accept_sampling"][:, -1] / 5000.0
+    assert abs(acc.mean() - 0.44) < 0.02
+
+
+def test_return_prior_all_transform_types():
+    """vignettes/checks_return_prior.Rmd: with a flat likelihood the four transform types return
+    N(0,1), -Gamma(5,5), Gamma(5,5), Beta(3,3)."""
+    df = drj.define_params("name", "real_line", "min", -np.inf, "max", np.inf, "name", "neg_line", "min", -np.inf, "max", 0,
+                           "name", "pos_line", "min", 0, "max", np.inf, "name", "unit_interval", "min", 0, "max", 1)
+    drj.use_builtin("returnprior")
+    res = drj.run_mcmc({"x": [1.0]}, df, loglike="loglike", logprior="logprior", burnin=1000, samples=4000, chains=256, seed=5,
+                       silent=True, as_frames=False)
+    th = res.raw["theta_sampling"][:, 0, ::40, :].reshape(-1, 4)  # thinned: ~independent draws
+    cdfs = [stats.norm(0, 1).cdf, lambda v: 1 - stats.gamma(5, scale=5).cdf(-v), stats.gamma(5, scale=5).cdf, stats.beta(3, 3).cdf]
+    for k, cdf in enumerate(cdfs):
+        assert stats.kstest(th[:, k], cdf).pvalue > 1e-4, k
+
+
+def test_tempering_mixes_the_double_well():
+    """vignettes/checks_double_well.Rmd: with 11 rungs (alpha = 2) the cold chain visits both wells."""
+    df = drj.define_params("name", "mu", "min", -2, "max", 2, "init", -1.0, "name", "gamma", "min", 30, "max", 30, "init", 30)
+    drj.use_builtin("doublewell")
+    res = drj.run_mcmc({"x": [-1.0]}, df, loglike="loglike", logprior="logprior", burnin=1000, samples=5000, rungs=11, alpha=2,
+                       chains=32, seed=7, silent=True, as_frames=False)
+    mu = res.raw["theta_sampling"][:, 0, :, 0]
+    frac_right = (mu > 0).mean(axis=1)
+    assert (frac_right > 0.2).all() and (frac_right < 0.8).all()
+    assert abs(np.abs(mu).mean() - 1.0) < 0.05
+    one = drj.run_mcmc({"x": [-1.0]}, df, loglike="loglike", logprior="logprior", burnin=1000, samples=5000, rungs=1, chains=32,
+                       seed=7, silent=True, as_frames=False)
+    # without rungs a chain stays in whichever well it was in at the end of burn-in
+    right = (one.raw["theta_sampling"][:, 0, :, 0] > 0).mean(axis=1)
+    assert np.all((right < 0.01) | (right > 0.99)) and (right < 0.01).mean() > 0.7
+
+
+def test_progress_callback_and_interrupt():
+    df = drj.define_params("name", "mu", "min", -np.inf, "max", np.inf)
+    drj.use_builtin("normal_mu")
+    seen = []
+    res = drj.run_mcmc({"x": [0.1, 0.2]}, df, loglike="loglike", logprior="logprior", burnin=200, samples=300, chains=2, seed=1,
+                       silent=True, progress=lambda phase, done, total: seen.append((phase, done, total)) and False)
+    assert seen[-1] == (1, 300, 300) and (0, 200, 200) in seen and len(seen) > 50
+    with pytest.raises(drj.DrjacobyError) as e:  # Rcpp::checkUserInterrupt analogue
+        drj.run_mcmc({"x": [0.1, 0.2]}, df, loglike="loglike", logprior="logprior", burnin=200, samples=300, chains=2, seed=1,
+                     silent=True, progress=lambda phase, done, total: done > 50)
+    assert e.value.code == 15

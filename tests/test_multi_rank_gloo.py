@@ -1,0 +1,59 @@
+"""N > 1 path on CPU: two gloo ranks shard the chains of one run_mcmc() call, run their slices and
+gather on rank 0.  The CPU oracle stands in for the CUDA engine (api._SHARD_RUNNER hook, tests only),
+so what is under test is the product's sharding, chain_offset bookkeeping and gather; the result must
+equal the unsharded run bit for bit (chains never interact; the Philox counter carries the global
+chain id)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    import drjacoby_b200 as drj
+    from drjacoby_b200 import api
+    from oracle import pyoracle
+    from test_host_api import oracle_runner
+    api._SHARD_RUNNER = oracle_runner(pyoracle)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = np.random.default_rng(1).normal(3, 2, 30)
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+    drj.use_builtin("example")
+    res = drj.run_mcmc({"x": x}, df, loglike="loglike", logprior="logprior", burnin=30, samples=40, rungs=3, chains=5,
+                       seed=11, cluster="torch", silent=True)
+    if rank == 0:
+        np.savez(os.path.join(tmpdir, "sharded.npz"), **res.raw, rhat=res.diagnostics["rhat"].to_numpy())
+    else:
+        assert res is None
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one(tmp_path, oracle):
+    import torch.multiprocessing as mp
+    import drjacoby_b200 as drj
+    from drjacoby_b200 import api
+    from test_host_api import oracle_runner
+    port = 29500 + (os.getpid() % 2000)
+    mp.start_processes(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
+    got = np.load(os.path.join(tmp_path, "sharded.npz"))
+    old = api._SHARD_RUNNER
+    api._SHARD_RUNNER = oracle_runner(oracle)
+    try:
+        x = np.random.default_rng(1).normal(3, 2, 30)
+        df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+        drj.use_builtin("example")
+        ref = drj.run_mcmc({"x": x}, df, loglike="loglike", logprior="logprior", burnin=30, samples=40, rungs=3, chains=5,
+                           seed=11, silent=True)
+    finally:
+        api._SHARD_RUNNER = old
+    for k, v in ref.raw.items():
+        if k != "t_diff":
+            assert np.array_equal(got[k], v), k
+    assert np.array_equal(got["rhat"], ref.diagnostics["rhat"].to_numpy())
