@@ -109,8 +109,9 @@ struct drj_model {
   bool jit = false;
   const void* init_fn = nullptr;   // built-in: __global__ function addresses
   const void* sweep_fn = nullptr;
+  const void* stream_fn = nullptr; // sweep variant for data streamed through shared memory (datum-form models)
   CUmodule module = nullptr;       // jit
-  CUfunction init_cu = nullptr, sweep_cu = nullptr;
+  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr;
   double compile_seconds = 0.0;
   int device = 0;
 };
@@ -121,12 +122,14 @@ struct BuiltinEntry {
   bool datum_form;
   const void* init_fn;
   const void* sweep_fn;
+  const void* stream_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
   {                                                                                      \
     NAME, __VA_ARGS__::D, __VA_ARGS__::NBLOCK, __VA_ARGS__::DATUM_FORM,                  \
-        (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__> \
+        (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__, false>, \
+        DrjStreamKernel<__VA_ARGS__>::get()                                                            \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -291,8 +294,12 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "  drj_init_body<DRJ_USER_MODEL>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  drj_sweep_body<DRJ_USER_MODEL>(a);\n"
-       "}\n";
+       "  drj_sweep_body<DRJ_USER_MODEL, false>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_stream(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void drj_user_traits(int* out) { out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0; }\n";
   return s;
 }
 
@@ -353,8 +360,22 @@ static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err)
     return set_err(err, DRJ_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
   }
   if (g_drv.ModuleGetFunction(&m->init_cu, m->module, "drj_user_init") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->sweep_cu, m->module, "drj_user_sweep") != CUDA_SUCCESS)
+      g_drv.ModuleGetFunction(&m->sweep_cu, m->module, "drj_user_sweep") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&m->stream_cu, m->module, "drj_user_sweep_stream") != CUDA_SUCCESS)
     return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
+  {  // does the user's model use the per-datum form?
+    CUfunction traits = nullptr;
+    int* d_flag = nullptr;
+    int h_flag = 0;
+    if (g_drv.ModuleGetFunction(&traits, m->module, "drj_user_traits") == CUDA_SUCCESS &&
+        cudaMalloc(&d_flag, sizeof(int)) == cudaSuccess) {
+      void* params[] = {(void*)&d_flag};
+      if (g_drv.LaunchKernel(traits, 1, 1, 1, 1, 1, 1, 0, nullptr, params, nullptr) == CUDA_SUCCESS &&
+          cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+        m->datum_form = h_flag != 0;
+      cudaFree(d_flag);
+    }
+  }
   return DRJ_OK;
 }
 
@@ -379,7 +400,7 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       if (desc->d > 0 && (b.D != desc->d || (desc->n_block > 0 && b.NBLOCK != desc->n_block))) continue;
       drj_model* m = new drj_model();
       m->name = b.name; m->D = b.D; m->NBLOCK = b.NBLOCK; m->datum_form = b.datum_form;
-      m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->device = device;
+      m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->stream_fn = b.stream_fn; m->device = device;
       *out = m;
       return DRJ_OK;
     }
@@ -444,6 +465,7 @@ struct drj_session {
   int *mc_b = nullptr, *mc_s = nullptr, *acc_b = nullptr;
   unsigned long long* err_key = nullptr;
   int64_t sweep_launches = 0, aux_launches = 0;
+  bool stream_variant = false;  // data too large for shared memory: use the streaming sweep kernel
   double t_create = 0.0;
   bool failed = false;
 };
@@ -502,8 +524,9 @@ static cudaError_t upload_list(drj_session* s, const drj_list* l, DrjList* out) 
 static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
   const drj_model* m = s->model;
   void* params[] = {(void*)&s->a};
+  const bool stream = sweep && s->stream_variant;
   if (m->jit) {
-    CUresult cr = g_drv.LaunchKernel(sweep ? m->sweep_cu : m->init_cu, s->grid, 1, 1, s->nthreads, 1, 1, 0,
+    CUresult cr = g_drv.LaunchKernel(!sweep ? m->init_cu : (stream ? m->stream_cu : m->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1, 0,
                                      (CUstream)s->stream, params, nullptr);
     if (cr != CUDA_SUCCESS) {
       const char* es = nullptr;
@@ -511,7 +534,8 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
       return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernel: %s", es ? es : "?");
     }
   } else {
-    CUDA_TRY(cudaLaunchKernel(sweep ? m->sweep_fn : m->init_fn, dim3(s->grid), dim3(s->nthreads), params, 0, s->stream));
+    CUDA_TRY(cudaLaunchKernel(!sweep ? m->init_fn : (stream ? m->stream_fn : m->sweep_fn), dim3(s->grid), dim3(s->nthreads),
+                              params, 0, s->stream));
   }
   return DRJ_OK;
 }
@@ -683,6 +707,11 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
                    "run needs %.1f GB of device memory (outputs %.1f GB) but %.1f GB are free: reduce iterations, "
                    "chains per call, or turn off store_pt / save_hot_draws",
                    need / 1e9, bytes_final / 1e9, (double)free_b / 1e9);
+
+  // datum-form model and a data item that cannot stay resident in the two tiles -> streaming kernel
+  if (model->datum_form && data && (model->jit ? model->stream_cu != nullptr : model->stream_fn != nullptr))
+    for (int k = 0; k < data->n_items; ++k)
+      if (data->lengths[k] > 2 * DRJ_TILE) s->stream_variant = true;
 
   // ---- uploads
   DrjKernelArgs& a = s->a;

@@ -128,6 +128,13 @@ __device__ __forceinline__ void drj_bulk_g2s(void* smem_dst, const void* gmem_sr
                : "memory");
 }
 
+// 128-bit shared-memory load whose position in the instruction stream the compiler must keep
+__device__ __forceinline__ double2 drj_lds2(unsigned smem_addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smem_addr));
+  return v;
+}
+
 // ------------------------------------------------------------------ model traits helpers
 // A model is a struct with
 //   static constexpr int D, NBLOCK;  static constexpr bool DATUM_FORM;
@@ -209,16 +216,19 @@ struct DrjAcc {
 template <class M, bool FULL>
 __device__ __forceinline__ void drj_accum_span(const typename M::Consts& k, const double* __restrict__ buf, int cnt,
                                                DrjAcc& A) {
-  const double2* t2 = reinterpret_cast<const double2*>(buf);
   const int n8 = FULL ? (DRJ_TILE / 8) : (cnt >> 3);
   if (n8 > 0) {
-    // software pipeline: the broadcast LDS.128s of group j+1 are in flight while group j is in the
-    // FP64 pipe (tools/fp64_pattern_probe2.cu).  The last trip prefetches 8 doubles past the span;
-    // the tile buffer carries 8 doubles of slack.
-    double2 c0 = t2[0], c1 = t2[1], c2 = t2[2], c3 = t2[3];
+    // software pipeline: the four broadcast LDS.128 of group j+1 are issued BEFORE the 16 DFMA of
+    // group j.  The loads are volatile inline PTX: with plain C++ loads ptxas sinks them to ~20
+    // cycles before their use and the warp stalls on them (profiles/README.md); pinned like this the
+    // pattern runs at 97 % of the DFMA peak in tools/fp64_pattern_probe3.cu.  The last trip
+    // prefetches 8 doubles past the span; the tile buffer carries 8 doubles of slack.
+    const unsigned base = drj_smem_addr(buf);
+    double2 c0 = drj_lds2(base), c1 = drj_lds2(base + 16), c2 = drj_lds2(base + 32), c3 = drj_lds2(base + 48);
 #pragma unroll 2
     for (int j = 0; j < n8; ++j) {
-      const double2 n0 = t2[4 * j + 4], n1 = t2[4 * j + 5], n2 = t2[4 * j + 6], n3 = t2[4 * j + 7];
+      const unsigned ad = base + 64u * (unsigned)j + 64u;
+      const double2 n0 = drj_lds2(ad), n1 = drj_lds2(ad + 16), n2 = drj_lds2(ad + 32), n3 = drj_lds2(ad + 48);
       A.a[0] = M::datum(k, c0.x, A.a[0]);
       A.a[1] = M::datum(k, c0.y, A.a[1]);
       A.a[2] = M::datum(k, c1.x, A.a[2]);
@@ -241,8 +251,8 @@ __device__ __forceinline__ void drj_accum_span(const typename M::Consts& k, cons
 // CTA-wide likelihood sweep: every thread evaluates ITS OWN theta against the SAME data item.
 // Must be called by all threads of the CTA (uniform control flow).
 template <class M>
-__device__ __noinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typename M::Consts& k,
-                                                 const double* __restrict__ g, long long n) {
+__device__ __forceinline__ double drj_sweep_item_inl(DrjTiles<M, true>& T, const typename M::Consts& k,
+                                                     const double* __restrict__ g, long long n) {
   double* const buf = drj_tile_buf<M>();
   unsigned long long* const full = drj_tile_bars<M>();
   DrjAcc A;
@@ -291,6 +301,14 @@ __device__ __noinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typena
   return A.total();
 }
 
+// out-of-line copy for the register-resident (non-STREAM) kernel, whose live particle state would
+// otherwise be dragged through the sweep's register allocation
+template <class M>
+__device__ __noinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typename M::Consts& k,
+                                              const double* __restrict__ g, long long n) {
+  return drj_sweep_item_inl<M>(T, k, g, n);
+}
+
 template <class M>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const DrjKernelArgs& a,
                                                    const double* theta, int block) {
@@ -331,6 +349,39 @@ struct DrjState {
 };
 
 #define DRJ_UNROLL_N(N) ((N) <= 8 ? (N) : 1)
+
+// particle state <-> its SoA slots in HBM (launch boundaries; and around a streamed data sweep)
+template <class M>
+__device__ __forceinline__ void drj_load_state(const DrjKernelArgs& a, DrjState<M>& s, long long p) {
+  constexpr int D = M::D, B = M::NBLOCK;
+  constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
+  const long long P = a.P;
+#pragma unroll UD
+  for (int i = 0; i < D; ++i) {
+    const long long o = (long long)i * P + p;
+    s.theta[i] = a.theta[o]; s.phi[i] = a.phi[o]; s.logbw[i] = a.logbw[o];
+    s.alo[i] = a.adj_lo[o]; s.ahi[i] = a.adj_hi[o]; s.bwi[i] = a.bw_index[o];
+  }
+#pragma unroll UB
+  for (int b = 0; b < B; ++b) s.llb[b] = a.ll_block[(long long)b * P + p];
+  s.ll = a.ll[p]; s.lp = a.lp[p]; s.acc = a.accept[p];
+}
+
+template <class M>
+__device__ __forceinline__ void drj_store_state(const DrjKernelArgs& a, const DrjState<M>& s, long long p) {
+  constexpr int D = M::D, B = M::NBLOCK;
+  constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
+  const long long P = a.P;
+#pragma unroll UD
+  for (int i = 0; i < D; ++i) {
+    const long long o = (long long)i * P + p;
+    a.theta[o] = s.theta[i]; a.phi[o] = s.phi[i]; a.logbw[o] = s.logbw[i];
+    a.adj_lo[o] = s.alo[i]; a.adj_hi[o] = s.ahi[i]; a.bw_index[o] = s.bwi[i];
+  }
+#pragma unroll UB
+  for (int b = 0; b < B; ++b) a.ll_block[(long long)b * P + p] = s.llb[b];
+  a.ll[p] = s.ll; a.lp[p] = s.lp; a.accept[p] = s.acc;
+}
 
 // ------------------------------------------------------------------ init kernel body
 // Particle::init + theta_to_phi + init_like for every (chain, rung); writes state and row 0 of the
@@ -415,7 +466,14 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
 
 // ------------------------------------------------------------------ sweep kernel body
 // n_iter iterations of: update every rung (Particle::update), store, Metropolis coupling.
-template <class M>
+//
+// STREAM = variant for data too large to stay in shared memory: the particle state is parked in its
+// HBM slots for the duration of every data sweep and reloaded after it, so that nothing but the
+// proposal (a dozen values) is live across the sweep and the sweep's inner loop gets the whole
+// register file for its software pipeline (with the state live ptxas squeezes the loop into the ~48
+// remaining registers and the LDS->DFMA distance collapses; profiles/README.md).  Costs ~0.3 KB of
+// HBM traffic per thread per sweep of n >= 4097 data points.
+template <class M, bool STREAM>
 __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
@@ -448,15 +506,9 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
   // ---- load state into registers
   DrjState<M> s;
-#pragma unroll UD
-  for (int i = 0; i < D; ++i) {
-    const long long o = (long long)i * P + p;
-    s.theta[i] = a.theta[o]; s.phi[i] = a.phi[o]; s.logbw[i] = a.logbw[o];
-    s.alo[i] = a.adj_lo[o]; s.ahi[i] = a.adj_hi[o]; s.bwi[i] = a.bw_index[o];
-  }
+  drj_load_state<M>(a, s, p);
 #pragma unroll UB
-  for (int b = 0; b < B; ++b) { s.llb[b] = a.ll_block[(long long)b * P + p]; s.llb_p[b] = s.llb[b]; }
-  s.ll = a.ll[p]; s.lp = a.lp[p]; s.acc = a.accept[p];
+  for (int b = 0; b < B; ++b) s.llb_p[b] = s.llb[b];
   const double beta = a.beta_raised[r];
   const double target = a.target_acceptance;
   const unsigned gchain_lo = (unsigned)(unsigned long long)(a.chain_offset + cc);
@@ -504,7 +556,18 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       // likelihood of the blocks this parameter belongs to (Particle.h:107-112)
       for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
         const int b = a.block_idx[j];
-        s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
+        if constexpr (STREAM) {
+          typename M::Consts k;
+          const bool fast = M::prepare(s.theta, a.misc, b, k);
+          const int item = M::datum_item(b);
+          const long long n = a.data.len(item);
+          if (active) drj_store_state<M>(a, s, p);                          // park (theta slot i holds theta')
+          const double acc = drj_sweep_item_inl<M>(T, k, a.data.item(item), n);  // uniform: all threads sweep
+          drj_load_state<M>(a, s, p);
+          s.llb_p[B == 1 ? 0 : b - 1] = fast ? M::finish(k, acc, n) : M::loglike(s.theta, a.data, a.misc, b);
+        } else {
+          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
+        }
       }
       double ll_p = 0.0;
 #pragma unroll UB
@@ -650,15 +713,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
   // ---- write state back
   if (active) {
-#pragma unroll UD
-    for (int i = 0; i < D; ++i) {
-      const long long o = (long long)i * P + p;
-      a.theta[o] = s.theta[i]; a.phi[o] = s.phi[i]; a.logbw[o] = s.logbw[i];
-      a.adj_lo[o] = s.alo[i]; a.adj_hi[o] = s.ahi[i]; a.bw_index[o] = s.bwi[i];
-    }
-#pragma unroll UB
-    for (int b = 0; b < B; ++b) a.ll_block[(long long)b * P + p] = s.llb[b];
-    a.ll[p] = s.ll; a.lp[p] = s.lp; a.accept[p] = s.acc;
+    drj_store_state<M>(a, s, p);
     if (do_couple && r < R - 1) a.mc_accept[chain * (R - 1) + r] += s_mc[tid];
   }
 }
@@ -668,7 +723,16 @@ template <class M>
 __global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant__ DrjKernelArgs a) {
   drj_init_body<M>(a);
 }
-template <class M>
+template <class M, bool STREAM>
 __global__ void __launch_bounds__(DRJ_NT, 2) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
-  drj_sweep_body<M>(a);
+  drj_sweep_body<M, STREAM>(a);
 }
+// address of the streaming variant (datum-form models only)
+template <class M, bool DF = M::DATUM_FORM>
+struct DrjStreamKernel {
+  static const void* get() { return nullptr; }
+};
+template <class M>
+struct DrjStreamKernel<M, true> {
+  static const void* get() { return (const void*)drj_sweep_kernel<M, true>; }
+};
