@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES] + \
-          ["-ldl", "-lpthread", "-lrt"]
+          ["-ldl", "-lpthread", "-lrt"] + os.environ.get("DRJ_EXTRA_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,25 +7,27 @@
 #pragma once
 #include "drj_sampler.cuh"
 
-// per-datum form of  sum_i R::dnorm(x_i, mean, sd, log=TRUE):  z = x*(1/sd) - mean/sd  (1 FMA),
-// acc = z*z + acc (1 FMA); constants hoisted out of the data loop.
+// per-datum form of  sum_i R::dnorm(x_i, mean, sd, log=TRUE) = -(n (log sqrt(2 pi) + log sd) + sum_i (x_i - mean)^2 / (2 sd^2)):
+// per datum  d = x - mean (1 DADD), acc = d*d + acc (1 DFMA); the scale 1/(2 sd^2) and the constants are
+// applied once in finish().  Two FP64-pipe instructions per datum, each with at most two distinct
+// source registers: the earlier form z = fma(x, 1/sd, -mean/sd) read three, and when ptxas put both
+// loop constants in the same register bank that copy of the loop ran ~2x slower (profiles/README.md).
 struct DrjNormConsts {
-  double a, b, lognorm;
+  double mean, half_inv_var, lognorm;
 };
 __device__ __forceinline__ bool drj_norm_prepare(double mean, double sd, DrjNormConsts& k) {
-  const double inv = 1.0 / sd;
-  k.a = inv;
-  k.b = -mean * inv;
+  k.mean = mean;
+  k.half_inv_var = 0.5 / (sd * sd);
   k.lognorm = DRJ_LN_SQRT_2PI + log(sd);
   // outside this range R::dnorm's edge-case branches matter: use the exact serial evaluation
   return (sd > 1e-150) && (sd < 1e150) && (fabs(mean) < 1e150);
 }
 __device__ __forceinline__ double drj_norm_datum(const DrjNormConsts& k, double x, double acc) {
-  const double z = fma(x, k.a, k.b);
-  return fma(z, z, acc);
+  const double d = x - k.mean;
+  return fma(d, d, acc);
 }
 __device__ __forceinline__ double drj_norm_finish(const DrjNormConsts& k, double acc, long long n) {
-  return -((double)n * k.lognorm + 0.5 * acc);
+  return -((double)n * k.lognorm + k.half_inv_var * acc);
 }
 __device__ __forceinline__ double drj_norm_serial(const double* x, long long n, double mean, double sd) {
   double ret = 0.0;
