@@ -26,6 +26,9 @@
 #ifndef DRJ_TILE
 #define DRJ_TILE 2048   // doubles per data tile (16 KB); two tiles are resident per CTA
 #endif
+#ifndef DRJ_MINB
+#define DRJ_MINB 2     // min resident 256-thread CTAs per SM of the register-resident sweep kernel (register cap)
+#endif
 #define DRJ_EXCH 4      // doubles per thread exchanged per shared-memory pass during a rung swap
 
 #ifndef DRJACOBY_B200_H  // the host side takes these from include/drjacoby_b200.h
@@ -724,7 +727,7 @@ __global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant_
   drj_init_body<M>(a);
 }
 template <class M, bool STREAM>
-__global__ void __launch_bounds__(DRJ_NT, 2) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
+__global__ void __launch_bounds__(DRJ_NT, (STREAM ? 2 : DRJ_MINB)) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
   drj_sweep_body<M, STREAM>(a);
 }
 // address of the streaming variant (datum-form models only)

@@ -36,6 +36,15 @@ CASES = {
                            burnin=100, samples=100),
     "example_rungs32_hot": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20)], beta=beta_ladder(32, 2.0),
                                 chains=9, save_hot_draws=True),
+    # launch-geometry edge cases: rungs not dividing the warp / CTA size, inactive threads, one chain, the
+    # maximum of 256 rungs (one chain per CTA)
+    "example_rungs33": Case("example", [-10, 0], [10, np.inf], data=[normal_data(17)], beta=beta_ladder(33), chains=7,
+                            burnin=12, samples=12),
+    "example_rungs129": Case("example", [-10, 0], [10, np.inf], data=[normal_data(9)], beta=beta_ladder(129, 3.0), chains=3,
+                             burnin=6, samples=6, save_hot_draws=True),
+    "example_rungs256": Case("example", [-10, 0], [10, np.inf], data=[normal_data(8)], beta=beta_ladder(256), chains=2,
+                             burnin=5, samples=5),
+    "example_one_chain": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100)], chains=1, burnin=300, samples=300),
     "example_coupling_off": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20)], beta=beta_ladder(3),
                                  chains=2, coupling_on=False),
     # data streamed through shared memory in tiles (n > 2 tiles), ragged last tile
