@@ -256,6 +256,12 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:  # DRAM bytes per launch of this kernel on this workload, from one `ncu --set full` capture (profiles/)
+            if args.n_data == N_DATA and chains == CHAINS_PER_GPU:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))["traffic_bytes_per_launch"]
+        except Exception:
+            pass
         n_cta = -(-chains // max(1, 128 // RUNGS))  # 128-thread CTAs: chains_per_cta = 128 // rungs
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
@@ -272,7 +278,7 @@ def run_ours(args):
             "gpu_launches": int((l1[0] - l0[0]) + (l1[1] - l0[1])),
             "launches": {"sweep": int(l1[0] - l0[0]), "transpose": int(l1[1] - l0[1])},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
-                         "traffic": None, "kernel": "drj_sweep_kernel<DrjModelExample, STREAM=true>",
+                         "traffic": traffic, "kernel": "drj_sweep_kernel<DrjModelExample, STREAM=true>",
                          "peak_source": "FP64 FMA probe (drj_fp64_peak_tflops) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
                          "algorithmic_flop_per_launch": flops_per_launch, "launch_ms": launch_s * 1e3,
                          "hbm": {"algorithmic_bytes_per_launch": 8.0 * args.n_data * D_FREE * n_cta, "peak_gbs": hbm_peak,
