@@ -133,6 +133,26 @@ def small_n_sweep(drj, device, chain_offset):
             "value": CHAINS_PER_GPU * RUNGS * D_FREE * 500 / (ms * 1e-3), "unit": UNIT}
 
 
+def target_regime_sweep(drj, device, chain_offset, fp64_peak):
+    """The north_star's joint target (>= 1e10 param-updates/s per 8-GPU box AT >= 70 % of the FP64 roofline)
+    is reachable only where the data sweep dominates the fixed per-update cost and n is small enough
+    (SURVEY 8(d)): n = 4096 (the largest data set that stays resident in shared memory), same 12,500 x 32
+    chain-rungs.  Roofline counts the sweep flops only (4 n per update)."""
+    n = 4096
+    x = synth_data(n)
+    spec = drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=default_init(CHAINS_PER_GPU, 78 + chain_offset),
+                       burnin=1, samples=60, beta_raised=np.linspace(0.0, 1.0, RUNGS), store_pt=False, rng_mode="philox",
+                       seed=2, chain_offset=chain_offset, device=device, data=[x], iters_per_launch=20)
+    s = drj.Session(drj.Model(builtin="example"), spec)
+    s.advance(20)
+    ms = s.advance(40)
+    s.close()
+    ups = CHAINS_PER_GPU * RUNGS * D_FREE * 40 / (ms * 1e-3)
+    tf = FLOP_PER_DATUM * n * ups / 1e12
+    return {"workload": f"normal model n={n}, 12500 chains x 32 rungs per GPU", "iterations": 40, "kernel_ms": ms, "value": ups,
+            "unit": UNIT + " per GPU", "per_8gpu_box_extrapolated": 8 * ups, "sweep_tflops": tf, "roofline_frac": tf / fp64_peak if fp64_peak else None}
+
+
 def ess_sweep(drj, device):
     """ESS/s (coda definition, min over parameters, summed over chains) on the K1 model: n=100, 1 rung,
     burnin 1e3 + samples 1e4, 1024 chains; ESS is evaluated on 64 chains and scaled."""
@@ -239,6 +259,7 @@ def run_ours(args):
     extra = {}
     if rank == 0 and not args.no_sweeps:
         extra["small_n"] = small_n_sweep(drj, device, chain_offset)
+        extra["target_regime"] = target_regime_sweep(drj, device, chain_offset, fp64_peak)
         extra["ess"] = ess_sweep(drj, device)
 
     cpu = None

@@ -708,10 +708,16 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
                    "chains per call, or turn off store_pt / save_hot_draws",
                    need / 1e9, bytes_final / 1e9, (double)free_b / 1e9);
 
-  // datum-form model and a data item that cannot stay resident in the two tiles -> streaming kernel
+  // datum-form model with a long data item -> the sweep-kernel variant that parks the particle state in
+  // HBM across data sweeps (mandatory when the item is streamed, n > 2 tiles; measured faster from
+  // n ~ 2048 on even when the data is resident in shared memory: tools/n_sweep.py)
   if (model->datum_form && data && (model->jit ? model->stream_cu != nullptr : model->stream_fn != nullptr))
     for (int k = 0; k < data->n_items; ++k)
-      if (data->lengths[k] > 2 * DRJ_TILE) s->stream_variant = true;
+      if (data->lengths[k] >= DRJ_TILE) s->stream_variant = true;
+  if (model->datum_form && (model->jit ? model->stream_cu != nullptr : model->stream_fn != nullptr)) {
+    if (cfg->flags & DRJ_FLAG_STREAM_KERNEL) s->stream_variant = true;    // tuning / testing overrides
+    if (cfg->flags & DRJ_FLAG_RESIDENT_KERNEL) s->stream_variant = false;
+  }
 
   // ---- uploads
   DrjKernelArgs& a = s->a;

@@ -93,6 +93,8 @@ typedef struct drj_config {
 } drj_config;
 
 #define DRJ_FLAG_NO_TMA 1    /* stage data tiles with plain loads instead of the TMA bulk-copy engine */
+#define DRJ_FLAG_STREAM_KERNEL 2   /* force the sweep-kernel variant that parks particle state in HBM across data sweeps */
+#define DRJ_FLAG_RESIDENT_KERNEL 4 /* force the variant that keeps particle state in registers (default unless data is streamed) */
 
 /* A model = the user's loglike + logprior (inst/templates/cpp_template.cpp:4-18).  Either a
  * built-in model (builtin != NULL) or CUDA source compiled at run time with NVRTC for sm_100a:
