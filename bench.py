@@ -97,7 +97,7 @@ def k5_spec(drj, x, chains, chain_offset, device, burnin, samples, seed=1):
 CPU_RUNGS = 8
 
 
-def cpu_baseline(x, cores, iters=2):
+def cpu_baseline(x, cores, iters=2, model="example"):
     """CPU oracle (a port of the reference's loop; the Rcpp reference itself cannot be built here: no R)
     on `cores` threads.  Bounded sample of the K5 workload: `cores` chains x CPU_RUNGS rungs x `iters`
     iterations on the full data.  The cost of a parameter update is one likelihood evaluation over the n
@@ -108,7 +108,7 @@ def cpu_baseline(x, cores, iters=2):
     po.build()
     chains = cores
     t0 = time.perf_counter()
-    po.run("example", [x], [], np.array([-10.0, 0.0]), np.array([10.0, np.inf]), default_init(chains, 1000),
+    po.run(model, [x], [], np.array([-10.0, 0.0]), np.array([10.0, np.inf]), default_init(chains, 1000),
            burnin=1, samples=iters, beta_raised=np.linspace(0.0, 1.0, CPU_RUNGS), rng_mode="philox", seed=1,
            n_threads=cores)
     dt = time.perf_counter() - t0
@@ -266,6 +266,9 @@ def run_ours(args):
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         cpu, _ = cpu_baseline(x if args.n_data <= N_DATA else x[:N_DATA], cores, iters=args.cpu_iters)
+        # the same with the reference's per-call copy of the data vector (example_loglike_logprior.cpp:12)
+        cpu_copy, _ = cpu_baseline(x if args.n_data <= N_DATA else x[:N_DATA], cores, iters=1, model="example_copy")
+        cpu["value_with_per_call_data_copy"] = cpu_copy["value"]
 
     if rank == 0:
         flops_per_launch = FLOP_PER_DATUM * args.n_data * chains * RUNGS * D_FREE  # one launch = one iteration
@@ -285,7 +288,7 @@ def run_ours(args):
             pass
         n_cta = -(-chains // max(1, 128 // RUNGS))  # 128-thread CTAs: chains_per_cta = 128 // rungs
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": UNIT, "chain_rung_updates_per_sec": value / D_FREE, "n_gpus": n_gpus, "steps": K, "warmup": W,
             "ms_per_step": dev_s / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"K5 shard: normal model (mu,sigma), n={args.n_data} data points, {chains} chains x {RUNGS} rungs per GPU "

@@ -722,6 +722,19 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   // ---- uploads
   DrjKernelArgs& a = s->a;
   memset(&a, 0, sizeof(a));
+  {  // chains inside one warp (rungs | 32) and no CTA-wide streamed sweep: per-warp synchronisation
+    bool streamed = false;
+    if (model->datum_form && data)
+      for (int k = 0; k < data->n_items; ++k) streamed = streamed || data->lengths[k] > 2 * DRJ_TILE;
+    // Per-warp mode puts one coupling walker in EVERY warp (about 25 x (R-1) issue slots per iteration at
+    // 1/32 lane efficiency) instead of packing the CTA's walkers into one warp, so it only pays when the
+    // update phase is long compared with the walk (measured: K4 +6 %, the 2-parameter n = 100 sweep -6 %).
+    int d_free_n = 0;
+    for (int i = 0; i < D; ++i) d_free_n += cfg->skip_param[i] ? 0 : 1;
+    a.warp_local = (32 % R == 0 && !streamed && !s->stream_variant && 6 * d_free_n > R - 1) ? 1 : 0;
+    if (const char* e = getenv("DRJ_WARP_LOCAL")) if (e[0] == '1' && 32 % R == 0 && !streamed && !s->stream_variant) a.warp_local = 1;
+    if (const char* e = getenv("DRJ_NO_WARP_LOCAL")) if (e[0] == '1') a.warp_local = 0;
+  }
   a.chains = C; a.rungs = R; a.chains_per_cta = cpc; a.coupling_on = cfg->coupling_on ? 1 : 0;
   a.save_hot_draws = cfg->save_hot_draws ? 1 : 0; a.store_pt = cfg->store_pt ? 1 : 0;
   a.rng_mode = cfg->rng_mode; a.d_free = s->d_free;

@@ -53,7 +53,7 @@ struct DrjKernelArgs {
   int rng_mode;        // 0 Philox, 1 replay
   int d_free;
   int use_tma;
-  int pad0;
+  int warp_local;      // rungs divide 32 and nothing in the loop needs a CTA barrier: chains sync per warp
   long long chain_offset;     // global id of chain 0 (Philox counter)
   unsigned long long seed;
   double target_acceptance;
@@ -467,6 +467,21 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
   }
 }
 
+// barrier of the coupling / abort phases: per warp when every chain lives inside one warp (R | 32)
+// and the kernel has no CTA-wide data sweep, so that the warps of a CTA run independently
+__device__ __forceinline__ void drj_sync(bool warp_local) {
+  if (warp_local) __syncwarp();
+  else __syncthreads();
+}
+__device__ __forceinline__ int drj_sync_or(bool warp_local, int pred) {
+  if (warp_local) {
+    const int any = __any_sync(0xffffffffu, pred);
+    __syncwarp();
+    return any;
+  }
+  return __syncthreads_or(pred);
+}
+
 // ------------------------------------------------------------------ sweep kernel body
 // n_iter iterations of: update every rung (Particle::update), store, Metropolis coupling.
 //
@@ -496,7 +511,9 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   __shared__ double s_logu[DRJ_NT];
   __shared__ short s_src[DRJ_NT];
   __shared__ int s_mc[DRJ_NT];
+  __shared__ double s_beta[DRJ_NT];
 
+  for (int i = tid; i < R; i += blockDim.x) s_beta[i] = a.beta_raised[i];
   for (int i = tid; i < D; i += blockDim.x) {
     s_tmin[i] = a.theta_min[i]; s_tmax[i] = a.theta_max[i];
     s_trans[i] = a.trans_type[i]; s_free[i] = a.free_slot[i];
@@ -518,6 +535,8 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   const unsigned gchain_hi = (unsigned)((unsigned long long)(a.chain_offset + cc) >> 32);
   const unsigned k0 = (unsigned)a.seed, k1 = (unsigned)(a.seed >> 32);
   const bool do_couple = a.coupling_on && R > 1;
+  const bool wl = a.warp_local != 0;
+  const int lane = tid & 31;
 
   for (int it = 0; it < a.n_iter; ++it) {
     const int t = a.iter0 + it;  // global update index, 1-based
@@ -638,34 +657,42 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         }
         s_logu[tid] = log(u);
       }
-      __syncthreads();
-      if (r == 0 && active) {
-        // sequential pass hot -> cold; the replica that is swapped upwards is carried along
+      drj_sync(wl);
+      // sequential pass hot -> cold, one chain per LANE of the first warp(s) (not one lane of every
+      // warp: the walk is ~20 instructions x (R-1) steps at 1/32 lane efficiency, and with one walker
+      // per warp it was 18 % of all issued instructions of the n = 100 sweep, profiles/README.md).
+      // warp_local: the first 32/R lanes of each warp walk that warp's chains.
+      // The replica that is swapped upwards is carried along.
+      const int wb = wl ? ((tid & ~31) + lane * R) : tid * R;
+      const int wlc = wb / R;
+      const bool walker = (wl ? (lane < 32 / R) : true) && wlc < a.chains_per_cta &&
+                          (long long)blockIdx.x * a.chains_per_cta + wlc < a.chains;
+      if (walker) {
         int cur_src = 0;
-        double cur_ll = s_x[base];
-        double b1 = a.beta_raised[0];
+        double cur_ll = s_x[wb];
+        double b1 = s_beta[0];
         for (int i = 0; i < R - 1; ++i) {
-          const double ll2 = s_x[base + i + 1];
-          const double b2 = a.beta_raised[i + 1];
+          const double ll2 = s_x[wb + i + 1];
+          const double b2 = s_beta[i + 1];
           double acceptance;
           if (b1 == 0.0) acceptance = (cur_ll * b2) - (ll2 * b2);
           else acceptance = (ll2 * b1 + cur_ll * b2) - (cur_ll * b1 + ll2 * b2);
-          if (s_logu[base + i] < acceptance) {
-            s_src[base + i] = (short)(i + 1);  // rung i receives the replica that sat at rung i+1
-            s_mc[base + i]++;
+          if (s_logu[wb + i] < acceptance) {
+            s_src[wb + i] = (short)(i + 1);  // rung i receives the replica that sat at rung i+1
+            s_mc[wb + i]++;
           } else {
-            s_src[base + i] = (short)cur_src;
+            s_src[wb + i] = (short)cur_src;
             cur_src = i + 1;
             cur_ll = ll2;
           }
           b1 = b2;
         }
-        s_src[base + R - 1] = (short)cur_src;
+        s_src[wb + R - 1] = (short)cur_src;
       }
-      __syncthreads();
+      drj_sync(wl);
       const int src = active ? (int)s_src[tid] : r;
       const int from = base + src;
-      if (__syncthreads_or(src != r)) {
+      if (drj_sync_or(wl, src != r)) {
         // replica-owned state moves: theta, phi, Jacobian logs, loglike_block, loglike, logprior.
         // rung-owned state stays: beta, bw, bw_index, accept_count (main.cpp:317-336).
         constexpr int NV = 4 * D + B + 2;
@@ -687,7 +714,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
               s_x[e * DRJ_NT + tid] = val;
             }
           }
-          __syncthreads();
+          drj_sync(wl);
 #pragma unroll
           for (int e = 0; e < DRJ_EXCH; ++e) {
             const int v = v0 + e;
@@ -702,7 +729,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
               else s.lp = val;
             }
           }
-          __syncthreads();
+          drj_sync(wl);
         }
       }
     }
@@ -710,9 +737,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
     // ================= abort on error (Rcpp::stop in the reference) =================
     // one barrier: own error, or (seen by thread 0) an error reported by any other CTA
     int stop = err;
-    if (tid == 0 && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
-    if (__syncthreads_or(stop)) break;
+    if ((wl ? lane == 0 : tid == 0) && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
+    if (drj_sync_or(wl, stop)) break;
   }
+  drj_sync(wl);
 
   // ---- write state back
   if (active) {

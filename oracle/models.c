@@ -7,6 +7,7 @@
  */
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "drj_oracle.h"
@@ -28,6 +29,21 @@ static double example_loglike(const double* p, int d, const ora_list* data, cons
 static double example_logprior(const double* p, int d, const ora_list* misc) {
   (void)d; (void)misc;
   return -log(20.0) + ora_dlnorm(p[1], 0.0, 1.0, 1);
+}
+
+/* Same model with the reference's per-call overhead that matters at large n: the whole data vector
+ * is copied on EVERY likelihood call (std::vector<double> x = Rcpp::as<...>(data["x"]),
+ * inst/extdata/example_loglike_logprior.cpp:12).  Used by bench.py as the "faithful overhead" baseline. */
+static double example_copy_loglike(const double* p, int d, const ora_list* data, const ora_list* misc, int block) {
+  (void)d; (void)misc; (void)block;
+  double mu = p[0], sigma = p[1];
+  int64_t n = item_len(data, 0);
+  double* x = (double*)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  memcpy(x, item(data, 0), sizeof(double) * (size_t)n);
+  double ret = 0.0;
+  for (int64_t i = 0; i < n; ++i) ret += ora_dnorm(x[i], mu, sigma, 1);
+  free(x);
+  return ret;
 }
 
 /* --- inst/extdata/coupling_loglike_logprior.cpp:5-37: params (alpha, beta, epsilon), data x */
@@ -173,6 +189,7 @@ static double halfdomain_logprior(const double* p, int d, const ora_list* misc) 
 static const ora_model MODELS[] = {
     {"example", example_loglike, example_logprior},
     {"example_exact", example_loglike, example_logprior},
+    {"example_copy", example_copy_loglike, example_logprior},
     {"coupling", coupling_loglike, coupling_logprior},
     {"blocks", blocks_loglike, blocks_logprior},
     {"doublewell", doublewell_loglike, zero_logprior},
