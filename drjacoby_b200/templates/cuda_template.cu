@@ -26,3 +26,37 @@ __device__ double logprior(const double* params, const DrjList& misc) {
 }
 
 // NOTE: if your functions are not called "loglike" / "logprior", pass their names to run_mcmc().
+
+// ---------------------------------------------------------------------------------------------
+// OPTIONAL: the per-datum form, for likelihoods that are a sum over many data points.
+// The functions above are evaluated by ONE GPU thread per chain x rung, which walks all the data
+// itself.  If instead you describe ONE term of the sum, the sampler stages the data once per thread
+// block in shared memory (streamed by the TMA engine when it does not fit) and all chains x rungs of
+// the block walk it together.  Define a struct like this and `#define DRJ_USER_MODEL` to its name
+// (loglike()/logprior() above are then unused and may be deleted):
+//
+//   struct MyModel {
+//     static constexpr int D = DRJ_D, NBLOCK = DRJ_NBLOCK;     // from df_params
+//     static constexpr bool DATUM_FORM = true;
+//     struct Consts { double mean, half_inv_var, lognorm; };   // whatever depends on params only
+//     __device__ static int datum_item(int block) { return DATA_x; }            // which data vector
+//     __device__ static bool prepare(const double* params, const DrjList& misc, int block, Consts& k) {
+//       k.mean = params[P_mu];  k.half_inv_var = 0.5 / (params[P_sigma] * params[P_sigma]);
+//       k.lognorm = 0.918938533204672741780329736406 + log(params[P_sigma]);
+//       return params[P_sigma] > 0;          // false -> loglike() below is used for this evaluation
+//     }
+//     __device__ static double datum(const Consts& k, double x, double acc) {   // acc += term(x)
+//       const double d = x - k.mean;  return fma(d, d, acc);
+//     }
+//     __device__ static double finish(const Consts& k, double acc, long long n) {
+//       return -((double)n * k.lognorm + k.half_inv_var * acc);
+//     }
+//     __device__ static double loglike(const double* params, const DrjList& data, const DrjList& misc, int block) {
+//       double r = 0; for (long long i = 0; i < data.len(DATA_x); ++i) r += R::dnorm(data.item(DATA_x)[i], params[P_mu], params[P_sigma], true);
+//       return r;                              // exact fallback, same value as prepare/datum/finish
+//     }
+//     __device__ static double logprior(const double* params, const DrjList& misc) { return 0.0; }
+//   };
+//   #define DRJ_USER_MODEL MyModel
+//
+// datum() must ADD its term to acc (the sampler keeps 8 partial sums and adds them at the end).

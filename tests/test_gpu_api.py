@@ -107,6 +107,50 @@ def test_nvrtc_user_model_equals_builtin():
     assert src.model("loglike", "logprior").compile_seconds() >= 0.0
 
 
+DATUM_SRC = r"""
+// a user model in the per-datum form (cuda_template.cu, second half): same arithmetic as the built-in "example"
+struct MyModel {
+  static constexpr int D = DRJ_D, NBLOCK = DRJ_NBLOCK;
+  static constexpr bool DATUM_FORM = true;
+  struct Consts { double mean, half_inv_var, lognorm; };
+  __device__ static int datum_item(int block) { return DATA_x; }
+  __device__ static bool prepare(const double* params, const DrjList& misc, int block, Consts& k) {
+    const double sd = params[P_sigma];
+    k.mean = params[P_mu];
+    k.half_inv_var = 0.5 / (sd * sd);
+    k.lognorm = 0.918938533204672741780329736406 + log(sd);
+    return (sd > 1e-150) && (sd < 1e150) && (fabs(k.mean) < 1e150);
+  }
+  __device__ static double datum(const Consts& k, double x, double acc) { const double d = x - k.mean; return fma(d, d, acc); }
+  __device__ static double finish(const Consts& k, double acc, long long n) { return -((double)n * k.lognorm + k.half_inv_var * acc); }
+  __device__ static double loglike(const double* params, const DrjList& data, const DrjList& misc, int block) {
+    double r = 0.0;
+    for (long long i = 0; i < data.len(DATA_x); ++i) r += R::dnorm(data.item(DATA_x)[i], params[P_mu], params[P_sigma], true);
+    return r;
+  }
+  __device__ static double logprior(const double* params, const DrjList& misc) { return -log(20.0) + R::dlnorm(params[P_sigma], 0.0, 1.0, true); }
+};
+#define DRJ_USER_MODEL MyModel
+"""
+
+
+@pytest.mark.parametrize("n", [100, 3000, 10001])
+def test_nvrtc_datum_form_user_model(n):
+    """A user model in the per-datum form through NVRTC: data resident in shared memory (n = 100), the
+    state-parking kernel variant (n = 3000) and TMA-streamed tiles (n = 10001); bitwise the built-in."""
+    x = np.random.default_rng(4).normal(3, 2, n)
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+    kw = dict(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=10, samples=15, rungs=4, chains=5,
+              seed=17, silent=True, as_frames=False)
+    drj.source_cuda(DATUM_SRC)
+    a = drj.run_mcmc(**kw)
+    drj.use_builtin("example")
+    b = drj.run_mcmc(**kw)
+    for k in a.raw:
+        if k != "t_diff":
+            assert np.array_equal(a.raw[k], b.raw[k]), k
+
+
 def test_nvrtc_errors_are_reported():
     df = drj.define_params("name", "mu", "min", -10, "max", 10)
     drj.source_cuda("__device__ double loglike(const double* p, const DrjList& d, const DrjList& m, int b) { return undefined_symbol; }\n"
