@@ -64,6 +64,12 @@ class DrjOutput(C.Structure):
     ]
 
 
+class DrjSummary(C.Structure):
+    _fields_ = [("max_lag", C.c_int32), ("reserved", C.c_int32), ("center", C.POINTER(C.c_double)),
+                ("chain_mean", C.POINTER(C.c_double)), ("chain_var", C.POINTER(C.c_double)),
+                ("autocov_sum", C.POINTER(C.c_double)), ("deviance_mean_var", C.POINTER(C.c_double))]
+
+
 class DrjError(C.Structure):
     _fields_ = [("code", C.c_int32), ("rung", C.c_int32), ("param", C.c_int32), ("iteration", C.c_int32),
                 ("chain", C.c_int64), ("theta", C.c_double * 64), ("message", C.c_char * 512)]
@@ -87,6 +93,7 @@ SYMBOLS = {
     "drj_session_advance": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(DrjError)]),
     "drj_session_iterations_done": (C.c_int, [C.c_void_p]),
     "drj_session_download": (C.c_int, [C.c_void_p, C.POINTER(DrjOutput), C.POINTER(DrjError)]),
+    "drj_session_summary": (C.c_int, [C.c_void_p, C.POINTER(DrjSummary), C.POINTER(DrjError)]),
     "drj_session_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "drj_session_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "drj_session_destroy": (None, [C.c_void_p]),

@@ -210,14 +210,16 @@ def _flatten_list(d: dict, what: str):
 def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3, samples=1e4, rungs=1, chains=5,
              beta_manual=None, alpha=1.0, target_acceptance=0.44, cluster=None, coupling_on=True, pb_markdown=False,
              save_data=True, save_hot_draws=False, silent=False, *, source: CudaSource | None = None, seed=None,
-             rng="philox", store_pt=True, device=None, as_frames=True, progress=None) -> DrjacobyOutput:
+             rng="philox", store_pt=True, device=None, as_frames=True, progress=None, output="full") -> DrjacobyOutput:
     """run_mcmc() of the reference (R/main.R:208-225) on the GPU.
 
     Extra keyword-only arguments: `source` (a CudaSource; default: the last source_cuda()/use_builtin()),
     `seed`, `rng` ("philox": counter-based device RNG; "r": R's set.seed(seed) stream generated on the
     host and replayed on the device, chain for chain what the reference would draw), `store_pt`
     (keep loglike/logprior of the heated rungs, as the reference always does), `device`, `as_frames`
-    (build the data frames; False keeps only `.raw` for very large runs).
+    (build the data frames; False keeps only `.raw` for very large runs), `output` ("full": every draw comes
+    back, as in the reference; "summary": the draws stay in GPU memory and Rhat / ESS / DIC are computed from
+    on-device reductions -- for runs whose draws are too large to move).
     `cluster`: None = this process's GPU; "torch" = shard chains over the ranks of an initialised
     torch.distributed group (one process per GPU), results gathered on rank 0.
     """
@@ -340,6 +342,18 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
             print(phase_names[phase], file=sys.stdout, flush=True)
         return 0
 
+    if output not in ("full", "summary"):
+        raise ValueError('output must be "full" or "summary"')
+    if output == "summary":
+        raw, diagnostics = _run_summary(model, spec, _progress if not (silent and progress is None) else None, names=list(df_params["name"]),
+                                        skip_param=skip_param, chains=chains, rank=rank, world=world, beta_raised=beta_raised)
+        if rank != 0:
+            return None
+        parameters = dict(data=data if save_data else None, df_params=df_params, loglike=loglike, logprior=logprior,
+                          burnin=burnin, samples=samples, rungs=rungs, chains=chains, coupling_on=bool(coupling_on), alpha=alpha,
+                          beta_manual=beta_manual)
+        diagnostics["wall_seconds"] = time.perf_counter() - t_start
+        return DrjacobyOutput(None, None, diagnostics, parameters, raw)
     raw = _run_shard(model, spec, None if (silent and progress is None) else _progress)
     if cluster is not None:
         raw = gather_shards(raw, chains, rank, world)
@@ -361,6 +375,81 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
     res = DrjacobyOutput(out["output"], out["pt"], out["diagnostics"], parameters, raw)
     res.diagnostics["wall_seconds"] = time.perf_counter() - t_start
     return res
+
+
+def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, world, beta_raised):
+    """output="summary": run the shard in a session, reduce the draws on the device, bring back only the
+    summaries and counters; across ranks the per-chain moments are gathered and the autocovariance sums
+    (about the global mean) added.  Pairs of draws that straddle two ranks' shards (at most order.max per
+    boundary out of chains x samples) are not counted."""
+    sess = engine.Session(model, spec)
+    try:
+        nb = spec.burnin - 1
+        for phase, total in ((0, nb), (1, spec.samples)):
+            step = max(1, (total + 99) // 100) if progress is not None else max(total, 1)
+            done = 0
+            while done < total:
+                n = min(step, total - done)
+                sess.advance(n)
+                done += n
+                if progress is not None and progress(None, phase, done + (1 if phase == 0 else 0), spec.burnin if phase == 0 else spec.samples):
+                    raise DrjacobyError(15, "interrupted by the progress callback")
+        n_tot = chains * spec.samples
+        max_lag = min(n_tot - 1, int(np.floor(10 * np.log10(n_tot))))
+        first = sess.summary(max_lag=0)
+        mean, var = first["chain_mean"], first["chain_var"]
+        dev = np.array([first["deviance_mean_var"][0], first["deviance_mean_var"][1], spec.chains * spec.samples], dtype=np.float64)
+        if world > 1:
+            parts = gather_shards({"m": mean, "v": var, "dev": dev[None, :]}, chains, rank, world)
+            import torch
+            import torch.distributed as dist
+            backend = dist.get_backend()
+            devc = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+            ctr_t = torch.zeros(spec.d, dtype=torch.float64, device=devc)
+            if rank == 0:
+                ctr_t += torch.from_numpy(parts["m"].mean(axis=0)).to(devc)
+            dist.broadcast(ctr_t, src=0)
+            center = ctr_t.cpu().numpy()
+        else:
+            parts = {"m": mean, "v": var, "dev": dev[None, :]}
+            center = mean.mean(axis=0)
+        ac = sess.summary(max_lag=max_lag, center=center)["autocov_sum"]
+        if world > 1:
+            t = torch.from_numpy(ac).to(devc)
+            dist.all_reduce(t)
+            ac = t.cpu().numpy()
+        raw = sess.download(draws=False)
+        if world > 1:
+            raw = gather_shards(raw, chains, rank, world)
+    finally:
+        sess.close()
+    if rank != 0:
+        return None, None
+    mean, var = parts["m"], parts["v"]
+    diagnostics = {"run_time": pd.DataFrame({"chain": np.arange(1, chains + 1), "seconds": raw["t_diff"]})}
+    if chains > 1 and spec.samples > 1:
+        diagnostics["rhat"] = pd.Series({nm: (np.nan if skip_param[k] else dg.gelman_rubin_from_moments(mean[:, k], var[:, k], spec.samples))
+                                         for k, nm in enumerate(names)})
+    diagnostics["ess"] = pd.Series({nm: (np.nan if skip_param[k] else dg.ess_from_autocov(ac[k], n_tot)) for k, nm in enumerate(names)})
+    diagnostics["rung_details"] = pd.DataFrame({"rung": np.arange(1, spec.rungs + 1), "thermodynamic_power": beta_raised})
+    if spec.rungs > 1:
+        link = np.tile(np.arange(1, spec.rungs), chains)
+        chain = np.repeat(np.arange(1, chains + 1), spec.rungs - 1)
+        diagnostics["mc_accept"] = pd.concat([
+            pd.DataFrame({"link": link, "chain": chain, "phase": "burnin", "value": raw["mc_accept_burnin"].ravel() / spec.burnin}),
+            pd.DataFrame({"link": link, "chain": chain, "phase": "sampling", "value": raw["mc_accept_sampling"].ravel() / spec.samples})],
+            ignore_index=True)
+    else:
+        diagnostics["mc_accept"] = np.nan
+    # deviance over all ranks: pool the per-rank (mean, variance, count)
+    d = parts["dev"]
+    n_all = d[:, 2].sum()
+    gm = (d[:, 0] * d[:, 2]).sum() / n_all
+    m2 = (d[:, 1] * (d[:, 2] - 1) + d[:, 2] * (d[:, 0] - gm) ** 2).sum()
+    diagnostics["DIC_Gelman"] = float(gm + 0.5 * m2 / (n_all - 1)) if n_all > 1 else np.nan
+    diagnostics["posterior_mean"] = pd.Series({nm: float(mean[:, k].mean()) for k, nm in enumerate(names)})
+    raw = dict(raw, chain_mean=mean, chain_var=var, autocov_sum=ac)
+    return raw, diagnostics
 
 
 def _printed_rate(acc, n, d):

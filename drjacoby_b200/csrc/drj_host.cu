@@ -85,6 +85,78 @@ __global__ void drj_export_bw(const double* __restrict__ logbw, long long P, int
   for (int i = 0; i < D; ++i) out[p * D + i] = exp(logbw[(long long)i * P + p]);
 }
 
+// ---- on-device summaries of the stored draws (R/main.R:498-554 without moving the draws)
+// series of chain c: x(c, t) = src[c * cs + t * ts], t < S
+__device__ __forceinline__ double drj_block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];  // fixed order: deterministic
+  __syncthreads();
+  if (threadIdx.x == 0) sh[0] = t;
+  __syncthreads();
+  t = sh[0];
+  return t;
+}
+
+// one CTA per (chain, series): mean and sample variance (two passes over the chain's S draws)
+__global__ void __launch_bounds__(256) drj_chain_moments(const double* __restrict__ src, long long cs, long long ts, long long ks,
+                                                        int S, int K, double* __restrict__ mean, double* __restrict__ var) {
+  __shared__ double sh[8];
+  const int c = blockIdx.x, k = blockIdx.y;
+  const double* x = src + (long long)c * cs + (long long)k * ks;
+  double a = 0.0;
+  for (int t = threadIdx.x; t < S; t += blockDim.x) a += x[(long long)t * ts];
+  const double m = drj_block_sum(a, sh) / (double)S;
+  double q = 0.0;
+  for (int t = threadIdx.x; t < S; t += blockDim.x) { const double d = x[(long long)t * ts] - m; q = fma(d, d, q); }
+  const double m2 = drj_block_sum(q, sh);
+  if (threadIdx.x == 0) { mean[(long long)c * K + k] = m; var[(long long)c * K + k] = S > 1 ? m2 / (double)(S - 1) : 0.0; }
+}
+
+// partial sums of (x_j - ctr)(x_{j+l} - ctr), l = l0 .. l0+15, over the chains CONCATENATED in chain order
+// (coda::effectiveSize is applied to the concatenated sampling draws, R/main.R:521-526)
+#define DRJ_LAGCH 16
+__global__ void __launch_bounds__(256) drj_autocov_partial(const double* __restrict__ src, long long cs, long long ts, int S,
+                                                          long long N, double ctr, int l0, int max_lag,
+                                                          double* __restrict__ partial /*[gridDim.x][DRJ_LAGCH]*/) {
+  __shared__ double sh[8];
+  double acc[DRJ_LAGCH];
+#pragma unroll
+  for (int q = 0; q < DRJ_LAGCH; ++q) acc[q] = 0.0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x) {
+    const long long c = j / S;
+    const int t = (int)(j - c * S);
+    const double xj = src[c * cs + (long long)t * ts] - ctr;
+    long long c2 = c;
+    long long t2 = (long long)t + l0;  // position of x_{j+l0}; rolls over chain boundaries
+    while (t2 >= S) { t2 -= S; ++c2; }
+#pragma unroll
+    for (int q = 0; q < DRJ_LAGCH; ++q) {
+      if (l0 + q <= max_lag && j + l0 + q < N) acc[q] = fma(xj, src[c2 * cs + t2 * ts] - ctr, acc[q]);
+      if (++t2 >= S) { t2 = 0; ++c2; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < DRJ_LAGCH; ++q) {
+    const double t = drj_block_sum(acc[q], sh);
+    if (threadIdx.x == 0) partial[(long long)blockIdx.x * DRJ_LAGCH + q] = t;
+  }
+}
+
+__global__ void drj_reduce_partials(const double* __restrict__ partial, int nblocks, double* __restrict__ out, int l0, int max_lag) {
+  const int q = threadIdx.x;
+  if (q < DRJ_LAGCH && l0 + q <= max_lag) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partial[(long long)b * DRJ_LAGCH + q];  // fixed order
+    out[l0 + q] = t;
+  }
+}
+
 // FP64 FMA throughput probe: 8 independent dependent-chains per thread
 __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
@@ -873,6 +945,73 @@ extern "C" int drj_session_timing(const drj_session* s, double* sweep_ms_total, 
   if (!s) return DRJ_ERR_ARG;
   if (sweep_ms_total) *sweep_ms_total = s->sweep_ms_total;
   if (stream_ms_total) *stream_ms_total = s->stream_ms_total;
+  return DRJ_OK;
+}
+
+extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* err) {
+  if (!s || !sm) return set_err(err, DRJ_ERR_ARG, "NULL session or summary");
+  if (sm->max_lag < 0 || sm->max_lag > 4096) return set_err(err, DRJ_ERR_ARG, "max_lag must be in [0, 4096]");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  const int D = s->D, C = s->C, S = s->cfg.samples;
+  const int thR = s->cfg.save_hot_draws ? s->R : 1, ptR = s->cfg.store_pt ? s->R : 1;
+  // cold rung, sampling phase: theta[(c*thR + thR-1)*S + t][k], loglike[(c*ptR + ptR-1)*S + t]
+  const double* th = s->fin_th_s + (long long)(thR - 1) * S * D;
+  const long long th_cs = (long long)thR * S * D, th_ts = D;
+  const double* ll = s->fin_ll_s + (long long)(ptR - 1) * S;
+  const long long ll_cs = (long long)ptR * S;
+  const long long N = (long long)C * S;
+  const int L = sm->max_lag;
+  double *d_mean = nullptr, *d_var = nullptr, *d_part = nullptr, *d_ac = nullptr, *d_lm = nullptr, *d_lv = nullptr;
+  const int nb = (int)std::min<long long>(2048, (N + 255) / 256);
+  cudaError_t e = cudaSuccess;
+  std::vector<double> mean((size_t)C * D), var((size_t)C * D), lm(C), lv(C), ac((size_t)L + 1);
+  auto cleanup = [&]() { cudaFree(d_mean); cudaFree(d_var); cudaFree(d_part); cudaFree(d_ac); cudaFree(d_lm); cudaFree(d_lv); };
+#define SUM_TRY(call) do { e = (call); if (e != cudaSuccess) { cleanup(); CUDA_TRY(e); } } while (0)
+  SUM_TRY(cudaMalloc(&d_mean, sizeof(double) * (size_t)C * D));
+  SUM_TRY(cudaMalloc(&d_var, sizeof(double) * (size_t)C * D));
+  SUM_TRY(cudaMalloc(&d_lm, sizeof(double) * (size_t)C));
+  SUM_TRY(cudaMalloc(&d_lv, sizeof(double) * (size_t)C));
+  SUM_TRY(cudaMalloc(&d_part, sizeof(double) * (size_t)nb * DRJ_LAGCH));
+  SUM_TRY(cudaMalloc(&d_ac, sizeof(double) * ((size_t)L + 1)));
+  drj_chain_moments<<<dim3(C, D), 256, 0, s->stream>>>(th, th_cs, th_ts, 1, S, D, d_mean, d_var);
+  drj_chain_moments<<<dim3(C, 1), 256, 0, s->stream>>>(ll, ll_cs, 1, 0, S, 1, d_lm, d_lv);
+  s->aux_launches += 2;
+  SUM_TRY(cudaMemcpyAsync(mean.data(), d_mean, sizeof(double) * mean.size(), cudaMemcpyDeviceToHost, s->stream));
+  SUM_TRY(cudaMemcpyAsync(var.data(), d_var, sizeof(double) * var.size(), cudaMemcpyDeviceToHost, s->stream));
+  SUM_TRY(cudaMemcpyAsync(lm.data(), d_lm, sizeof(double) * lm.size(), cudaMemcpyDeviceToHost, s->stream));
+  SUM_TRY(cudaMemcpyAsync(lv.data(), d_lv, sizeof(double) * lv.size(), cudaMemcpyDeviceToHost, s->stream));
+  SUM_TRY(cudaStreamSynchronize(s->stream));
+  if (sm->chain_mean) memcpy(sm->chain_mean, mean.data(), sizeof(double) * mean.size());
+  if (sm->chain_var) memcpy(sm->chain_var, var.data(), sizeof(double) * var.size());
+  if (sm->deviance_mean_var) {
+    // D = -2 loglike over all chains: mean and sample variance from the per-chain moments (equal lengths)
+    double gm = 0.0;
+    for (int c = 0; c < C; ++c) gm += lm[c];
+    gm /= C;
+    double m2 = 0.0;
+    for (int c = 0; c < C; ++c) m2 += lv[c] * (S - 1) + (double)S * (lm[c] - gm) * (lm[c] - gm);
+    sm->deviance_mean_var[0] = -2.0 * gm;
+    sm->deviance_mean_var[1] = N > 1 ? 4.0 * m2 / (double)(N - 1) : 0.0;
+  }
+  if (sm->autocov_sum) {
+    for (int k = 0; k < D; ++k) {
+      double ctr;
+      if (sm->center) ctr = sm->center[k];
+      else { ctr = 0.0; for (int c = 0; c < C; ++c) ctr += mean[(size_t)c * D + k]; ctr /= C; }
+      for (int l0 = 0; l0 <= L; l0 += DRJ_LAGCH) {
+        drj_autocov_partial<<<nb, 256, 0, s->stream>>>(th + k, th_cs, th_ts, S, N, ctr, l0, L, d_part);
+        drj_reduce_partials<<<1, 32, 0, s->stream>>>(d_part, nb, d_ac, l0, L);
+        s->aux_launches += 2;
+      }
+      SUM_TRY(cudaMemcpyAsync(ac.data(), d_ac, sizeof(double) * ac.size(), cudaMemcpyDeviceToHost, s->stream));
+      SUM_TRY(cudaStreamSynchronize(s->stream));
+      memcpy(sm->autocov_sum + (size_t)k * (L + 1), ac.data(), sizeof(double) * ac.size());
+    }
+  }
+  SUM_TRY(cudaGetLastError());
+#undef SUM_TRY
+  cleanup();
   return DRJ_OK;
 }
 

@@ -75,6 +75,35 @@ def ess(x) -> float:
     return 0.0 if spec == 0.0 else float(x.size * x.var(ddof=1) / spec)
 
 
+def gelman_rubin_from_moments(chain_mean, chain_var, samples: int) -> float:
+    """gelman_rubin() from per-chain means and sample variances (equal chain lengths)."""
+    m = np.asarray(chain_mean, dtype=np.float64)
+    v = np.asarray(chain_var, dtype=np.float64)
+    chains = m.size
+    if chains <= 1:
+        raise ValueError("chains must be greater than 1")
+    W = v.sum() / chains
+    Bv = samples / (chains - 1) * np.square(m - m.mean()).sum()
+    V = (1.0 - 1.0 / samples) * W + Bv / samples
+    return float(np.round(np.sqrt(V / W), 4))
+
+
+def ess_from_autocov(autocov_sum, n: int) -> float:
+    """coda::effectiveSize from the autocovariance SUMS sum_j (x_j - mean)(x_{j+l} - mean), l = 0..order.max,
+    of a series of length n (the sums come from the device, drj_session_summary)."""
+    r = np.asarray(autocov_sum, dtype=np.float64) / n
+    if not r[0] > 0.0:
+        return 0.0
+    pmax = r.size - 1
+    coefs, v = _levinson(r)
+    aic = n * np.log(v) + 2.0 * np.arange(pmax + 1) + 2.0
+    order = int(np.argmin(aic))
+    var_pred = v[order] * n / (n - (order + 1))
+    spec0 = var_pred / (1.0 - coefs[order].sum()) ** 2
+    var1 = r[0] * n / (n - 1)
+    return float(n * var1 / spec0)
+
+
 def dic_gelman(loglike) -> float:
     dev = -2.0 * np.asarray(loglike, dtype=np.float64).ravel()
     return float(dev.mean() + 0.5 * dev.var(ddof=1))

@@ -167,12 +167,19 @@ class RunSpec:
             t_diff=np.zeros(C_), bw_final=np.zeros((C_, R, d)))
 
 
+_DRAW_KEYS = ("loglike_burnin", "logprior_burnin", "theta_burnin", "loglike_sampling", "logprior_sampling", "theta_sampling")
+
+
 def _c_output(o: dict) -> L.DrjOutput:
-    return L.DrjOutput(
-        L.dptr(o["loglike_burnin"]), L.dptr(o["logprior_burnin"]), L.dptr(o["theta_burnin"]),
-        L.dptr(o["loglike_sampling"]), L.dptr(o["logprior_sampling"]), L.dptr(o["theta_sampling"]),
-        L.iptr(o["mc_accept_burnin"]), L.iptr(o["mc_accept_sampling"]), L.iptr(o["accept_burnin"]),
-        L.iptr(o["accept_sampling"]), L.dptr(o["t_diff"]), L.dptr(o["bw_final"]))
+    def dp(k):
+        return L.dptr(o[k]) if k in o else None
+
+    def ip(k):
+        return L.iptr(o[k]) if k in o else None
+
+    return L.DrjOutput(dp("loglike_burnin"), dp("logprior_burnin"), dp("theta_burnin"), dp("loglike_sampling"),
+                       dp("logprior_sampling"), dp("theta_sampling"), ip("mc_accept_burnin"), ip("mc_accept_sampling"),
+                       ip("accept_burnin"), ip("accept_sampling"), dp("t_diff"), dp("bw_final"))
 
 
 def run_raw(model: Model, spec: RunSpec, progress=None) -> dict:
@@ -228,8 +235,36 @@ class Session:
         L.lib().drj_session_timing(self._h, C.byref(a), C.byref(b))
         return float(a.value), float(b.value)
 
-    def download(self) -> dict:
+    def summary(self, max_lag: int | None = None, center=None) -> dict:
+        """On-device summaries of the cold-rung sampling draws (drj_session_summary): per-chain means and
+        variances, autocovariance sums of the concatenated chains, deviance mean / variance."""
+        sp = self.spec
+        n_tot = sp.chains * sp.samples
+        if max_lag is None:
+            max_lag = min(n_tot - 1, int(np.floor(10 * np.log10(n_tot))))  # stats::ar's order.max
+        out = dict(chain_mean=np.zeros((sp.chains, sp.d)), chain_var=np.zeros((sp.chains, sp.d)),
+                   autocov_sum=np.zeros((sp.d, max_lag + 1)), deviance_mean_var=np.zeros(2))
+        sm = L.DrjSummary()
+        sm.max_lag = int(max_lag)
+        ctr = None
+        if center is not None:
+            ctr = np.ascontiguousarray(center, dtype=np.float64)
+            sm.center = L.dptr(ctr)
+        sm.chain_mean, sm.chain_var = L.dptr(out["chain_mean"]), L.dptr(out["chain_var"])
+        sm.autocov_sum, sm.deviance_mean_var = L.dptr(out["autocov_sum"]), L.dptr(out["deviance_mean_var"])
+        err = L.DrjError()
+        rc = L.lib().drj_session_summary(self._h, C.byref(sm), C.byref(err))
+        L.raise_for(rc, err, sp.d)
+        out["max_lag"] = int(max_lag)
+        return out
+
+    def download(self, draws: bool = True) -> dict:
+        """All outputs, or (draws=False) only the counters / run times / bandwidths: the stored draws stay
+        on the device (summary mode for runs whose draws are too large to move)."""
         out = self.spec.alloc_outputs()
+        if not draws:
+            for k in _DRAW_KEYS:
+                del out[k]
         cout = _c_output(out)
         err = L.DrjError()
         rc = L.lib().drj_session_download(self._h, C.byref(cout), C.byref(err))

@@ -133,6 +133,19 @@ typedef struct drj_output {
   double* bw_final;            /* [chains][rungs][d] final proposal bandwidths; may be NULL */
 } drj_output;
 
+/* On-device summaries of the stored cold-rung sampling draws: what R/main.R:498-554 computes from the
+ * full data frames (Rhat from per-chain means/variances, ESS from the autocovariances of the
+ * concatenated chains, DIC from the deviance moments), without moving the draws to the host. */
+typedef struct drj_summary {
+  int32_t max_lag;           /* in: autocovariance lags 0..max_lag (coda uses floor(10 log10 N)) */
+  int32_t reserved;
+  const double* center;      /* in: [d] centre of the autocovariance sums; NULL = mean over this call's chains */
+  double* chain_mean;        /* out [chains][d]; may be NULL */
+  double* chain_var;         /* out [chains][d] sample variance (n-1); may be NULL */
+  double* autocov_sum;       /* out [d][max_lag+1]: sum_j (x_j - c)(x_{j+l} - c), chains concatenated; may be NULL */
+  double* deviance_mean_var; /* out [2]: mean and sample variance of -2 loglike; may be NULL */
+} drj_summary;
+
 typedef struct drj_error {
   int32_t code;
   int32_t rung;      /* 0-based */
@@ -173,7 +186,8 @@ int drj_session_create(const drj_config* cfg, const drj_model* model, const drj_
  * time of the sweep kernels of this call, measured on the session's stream */
 int drj_session_advance(drj_session* s, int n_iter, float* kernel_ms, drj_error* err);
 int drj_session_iterations_done(const drj_session* s); /* rows stored so far, incl. the initial row */
-int drj_session_download(drj_session* s, drj_output* out, drj_error* err);
+int drj_session_download(drj_session* s, drj_output* out, drj_error* err); /* NULL members of *out are skipped */
+int drj_session_summary(drj_session* s, drj_summary* summary, drj_error* err);
 int drj_session_launches(const drj_session* s, int64_t* sweep_launches, int64_t* aux_launches);
 /* cumulative CUDA-event time on the session's stream: sweep kernels only / sweep kernels + output transposes */
 int drj_session_timing(const drj_session* s, double* sweep_ms_total, double* stream_ms_total);

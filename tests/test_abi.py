@@ -33,8 +33,9 @@ def test_struct_sizes_match_the_header():
     import subprocess
     import tempfile
     from drjacoby_b200 import _lib
-    src = ('#include <stdio.h>\n#include "drjacoby_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(drj_config), '
-           'sizeof(drj_list), sizeof(drj_model_desc), sizeof(drj_output), sizeof(drj_error));return 0;}\n')
+    src = ('#include <stdio.h>\n#include "drjacoby_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu ", sizeof(drj_config), '
+           'sizeof(drj_list), sizeof(drj_model_desc), sizeof(drj_output), sizeof(drj_error));'
+           'printf("%zu\\n", sizeof(drj_summary));return 0;}\n')
     with tempfile.TemporaryDirectory() as td:
         c = os.path.join(td, "t.c")
         open(c, "w").write(src)
@@ -42,7 +43,7 @@ def test_struct_sizes_match_the_header():
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
     assert sizes == [C.sizeof(_lib.DrjConfig), C.sizeof(_lib.DrjList), C.sizeof(_lib.DrjModelDesc),
-                     C.sizeof(_lib.DrjOutput), C.sizeof(_lib.DrjError)]
+                     C.sizeof(_lib.DrjOutput), C.sizeof(_lib.DrjError), C.sizeof(_lib.DrjSummary)]
 
 
 def test_builtin_models_cover_the_reference_model_files():

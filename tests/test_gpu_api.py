@@ -275,3 +275,29 @@ def test_progress_callback_and_interrupt():
         drj.run_mcmc({"x": [0.1, 0.2]}, df, loglike="loglike", logprior="logprior", burnin=200, samples=300, chains=2, seed=1,
                      silent=True, progress=lambda phase, done, total: done > 50)
     assert e.value.code == 15
+
+
+def test_summary_mode_matches_full_mode():
+    """output="summary": Rhat / ESS / DIC from on-device reductions of the stored draws equal the host
+    post-processing of the downloaded draws (R/main.R:498-554) -- same run, draws never leave the GPU."""
+    x = np.random.default_rng(3).normal(3, 2, 40)
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf,
+                           "name", "fixed", "min", 2, "max", 2)
+    src = drj.source_cuda(NORMAL_SRC)
+    kw = dict(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=300, samples=1500, rungs=4, chains=7,
+              seed=21, silent=True)
+    full = drj.run_mcmc(**kw)
+    summ = drj.run_mcmc(output="summary", **kw)
+    assert summ.output is None and summ.pt is None and "theta_sampling" not in summ.raw
+    for k in ("mu", "sigma"):
+        assert summ.diagnostics["rhat"][k] == full.diagnostics["rhat"][k]
+        assert abs(summ.diagnostics["ess"][k] - full.diagnostics["ess"][k]) <= 1e-8 * full.diagnostics["ess"][k]
+    assert np.isnan(summ.diagnostics["rhat"]["fixed"]) and np.isnan(summ.diagnostics["ess"]["fixed"])
+    assert abs(summ.diagnostics["DIC_Gelman"] - full.diagnostics["DIC_Gelman"]) <= 1e-10 * abs(full.diagnostics["DIC_Gelman"])
+    assert np.array_equal(summ.raw["accept_sampling"], full.raw["accept_sampling"])
+    assert np.array_equal(summ.raw["mc_accept_sampling"], full.raw["mc_accept_sampling"])
+    th = full.raw["theta_sampling"][:, 0]
+    np.testing.assert_allclose(summ.raw["chain_mean"], th.mean(axis=1), rtol=1e-12)
+    np.testing.assert_allclose(summ.raw["chain_var"][:, :2], th.var(axis=1, ddof=1)[:, :2], rtol=1e-10)
+    pd_mc = summ.diagnostics["mc_accept"]
+    assert pd_mc["value"].tolist() == full.diagnostics["mc_accept"]["value"].tolist()
