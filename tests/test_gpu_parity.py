@@ -205,3 +205,29 @@ def test_halfdomain_semantics():
     out2 = run_gpu(CASES["halfdomain_prior"], "philox", seed=1)
     th2 = np.concatenate([out2["theta_burnin"], out2["theta_sampling"]], axis=2)[..., 0]
     assert (th2 <= 0.5).all()
+
+
+def test_random_configurations_match_oracle(oracle):
+    """Differential fuzz: 40 random launch shapes / options (rungs 1..40, chains 1..37, data sizes around the
+    accumulator-group, tile and residency boundaries, bounds, coupling on/off, hot draws, targets, seeds)."""
+    rng = np.random.Generator(np.random.Philox(2024))
+    sizes = [1, 2, 7, 8, 9, 15, 16, 17, 63, 100, 255, 2047, 2048, 2049, 4095, 4096, 4097, 6151]
+    for trial in range(40):
+        n = int(rng.choice(sizes))
+        R = int(rng.integers(1, 41))
+        chains = int(rng.integers(1, 38))
+        iters = 6 if n > 2000 else int(rng.integers(5, 40))
+        model = ["example", "example_exact", "testfile"][int(rng.integers(0, 3))] if n <= 300 else "example"
+        lo = float(rng.choice([-10.0, -3.0, 0.5]))
+        tmin, tmax = [lo, 0.0], [lo + float(rng.choice([2.0, 20.0])), float(rng.choice([np.inf, 50.0]))]
+        case = Case(model, tmin, tmax, data=[normal_data(n, seed=100 + trial, mean=lo + 1.0, sd=1.5)],
+                    beta=beta_ladder(R, float(rng.choice([1.0, 2.0, 3.5]))), chains=chains, burnin=iters, samples=iters,
+                    coupling_on=bool(rng.integers(0, 2)), save_hot_draws=bool(rng.integers(0, 2)),
+                    target=float(rng.choice([0.1, 0.44, 0.8])), seed=trial)
+        seed, off = int(rng.integers(0, 2**40)), int(rng.integers(0, 10**6))
+        kw = {}
+        if rng.integers(0, 2):
+            kw["iters_per_launch"] = int(rng.integers(1, 9))
+        ora = run_oracle(oracle, case, "philox", seed=seed, chain_offset=off)
+        gpu = run_gpu(case, "philox", seed=seed, chain_offset=off, **kw)
+        assert_parity(gpu, ora, RTOL, what=f"[fuzz {trial}: {model} n={n} R={R} C={chains} {kw}] ")
