@@ -361,7 +361,10 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
             return None
     if not silent:
         d_all = d
-        for c in range(chains):  # src/main.cpp:147-150,194-197,253-257
+        shown = chains if chains <= 20 else 5  # the reference prints every chain; thousands of chains would flood
+        if shown < chains:
+            print(f"(acceptance rates of the first {shown} of {chains} chains)")
+        for c in range(shown):  # src/main.cpp:147-150,194-197,253-257
             print(f"MCMC chain {c + 1}")
             print(f"burn-in\nacceptance rate: {_printed_rate(raw['accept_burnin'][c, -1], burnin, d_all)}%")
             print(f"sampling phase\nacceptance rate: {_printed_rate(raw['accept_sampling'][c, -1], samples, d_all)}%")

@@ -538,6 +538,7 @@ struct drj_session {
   unsigned long long* err_key = nullptr;
   int64_t sweep_launches = 0, aux_launches = 0;
   bool stream_variant = false;  // data too large for shared memory: use the streaming sweep kernel
+  unsigned dyn_smem = 0;        // dynamic shared memory of the model kernels: the data tile buffer
   double t_create = 0.0;
   bool failed = false;
 };
@@ -598,7 +599,7 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
   void* params[] = {(void*)&s->a};
   const bool stream = sweep && s->stream_variant;
   if (m->jit) {
-    CUresult cr = g_drv.LaunchKernel(!sweep ? m->init_cu : (stream ? m->stream_cu : m->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1, 0,
+    CUresult cr = g_drv.LaunchKernel(!sweep ? m->init_cu : (stream ? m->stream_cu : m->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1, s->dyn_smem,
                                      (CUstream)s->stream, params, nullptr);
     if (cr != CUDA_SUCCESS) {
       const char* es = nullptr;
@@ -607,7 +608,7 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
     }
   } else {
     CUDA_TRY(cudaLaunchKernel(!sweep ? m->init_fn : (stream ? m->stream_fn : m->sweep_fn), dim3(s->grid), dim3(s->nthreads),
-                              params, 0, s->stream));
+                              params, s->dyn_smem, s->stream));
   }
   return DRJ_OK;
 }
@@ -789,6 +790,17 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   if (model->datum_form && (model->jit ? model->stream_cu != nullptr : model->stream_fn != nullptr)) {
     if (cfg->flags & DRJ_FLAG_STREAM_KERNEL) s->stream_variant = true;    // tuning / testing overrides
     if (cfg->flags & DRJ_FLAG_RESIDENT_KERNEL) s->stream_variant = false;
+  }
+
+  // dynamic shared memory = the data tile buffer of datum-form models: the longest item if every item
+  // stays resident (<= 2 tiles), else two tiles; + 8 doubles of slack for the pipelined prefetch
+  if (model->datum_form && data) {
+    long long longest = 0;
+    for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
+    // (the kernels keep the data resident only for single-block models: DrjTiles::init)
+    const bool resident = model->NBLOCK == 1 && longest <= 2 * DRJ_TILE;
+    const long long doubles = (resident ? ((longest + 1) & ~1LL) : 2LL * DRJ_TILE) + 8;
+    s->dyn_smem = (unsigned)(doubles * sizeof(double));
   }
 
   // ---- uploads

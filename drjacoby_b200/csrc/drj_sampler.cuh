@@ -156,10 +156,13 @@ struct DrjTiles {  // no tiles for generic models
 // The tile buffers and their mbarriers are static shared memory owned by these two accessors, so
 // that every user (kernel body, the noinline sweep routine) sees a pointer the compiler KNOWS is
 // shared memory (a pointer carried through a struct degrades to generic LD.E loads).
+// The buffer itself is DYNAMIC shared memory sized by the host (drj_tile_smem_bytes): the whole data
+// item + slack when it stays resident (n <= 2 tiles), two tiles + slack when it is streamed -- a small
+// data set must not cost 32 KB per CTA and cap the number of resident CTAs.
+extern __shared__ __align__(128) double drj_dyn_smem[];
 template <class M>
 __device__ __forceinline__ double* drj_tile_buf() {
-  __shared__ __align__(128) double s_buf[2 * DRJ_TILE + 8];  // + slack for the pipelined prefetch
-  return s_buf;
+  return drj_dyn_smem;
 }
 template <class M>
 __device__ __forceinline__ unsigned long long* drj_tile_bars() {
