@@ -39,9 +39,18 @@ _PARAM_KEYS = ("name", "min", "max", "init", "block")
 _CURRENT_SOURCE: dict[str, Any] = {"model": None}
 
 
-def cuda_template() -> str:
-    """The CUDA analogue of cpp_template(): text of drjacoby_b200/templates/cuda_template.cu."""
-    return open(os.path.join(os.path.dirname(__file__), "templates", "cuda_template.cu")).read()
+def cuda_template(save_as: str | None = None) -> str:
+    """The CUDA analogue of cpp_template(save_as) (R/cpp_template.R:6-18): writes the model template to
+    `save_as` (must end in .cu) and returns its text; with no argument just returns the text."""
+    text = open(os.path.join(os.path.dirname(__file__), "templates", "cuda_template.cu")).read()
+    if save_as is not None:
+        if not isinstance(save_as, str):
+            raise TypeError("save_as must be a single character string")
+        if os.path.splitext(save_as)[1] != ".cu":
+            raise ValueError("File must be .cu")
+        with open(save_as, "w") as f:
+            f.write(text)
+    return text
 
 
 def source_cuda(code_or_path: str) -> "CudaSource":
