@@ -115,6 +115,7 @@ struct DrjModelMultilevel {
   __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int block) {
     double ret = 0.0;
     if (block == G + 1) {
+#pragma unroll 10
       for (int i = 0; i < G; ++i) ret += R::dnorm(th[i], 0.0, 1.0, 1);
     } else {
       const double* x = data.item(block - 1);

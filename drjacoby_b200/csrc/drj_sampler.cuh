@@ -354,7 +354,10 @@ struct DrjState {
   int acc;
 };
 
-#define DRJ_UNROLL_N(N) ((N) <= 8 ? (N) : 1)
+// small arrays: full unroll (state stays in registers); large arrays live in local memory anyway, and a
+// partial unroll of 8 lets the loads of a copy / sum loop overlap instead of paying the L1/L2 latency one
+// by one (K4, d = 50: long_scoreboard was 7.2 stalls per issue, profiles/README.md)
+#define DRJ_UNROLL_N(N) ((N) <= 8 ? (N) : 8)
 
 // particle state <-> its SoA slots in HBM (launch boundaries; and around a streamed data sweep)
 template <class M>
@@ -547,7 +550,8 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
     const double* rp = a.rng_mode ? a.replay + (cc * a.replay_T + (t - 1)) * a.replay_U : nullptr;
 
     // ================= Particle::update =================
-#pragma unroll UD
+    constexpr int UP = (D <= 8) ? D : 1;  // the update body itself is only unrolled for small d
+#pragma unroll UP
     for (int i = 0; i < D; ++i) {
       const int fs = s_free[i];
       if (fs < 0) continue;  // skip_param: no RNG consumed (Particle.h:91-93)
