@@ -301,3 +301,34 @@ def test_summary_mode_matches_full_mode():
     np.testing.assert_allclose(summ.raw["chain_var"][:, :2], th.var(axis=1, ddof=1)[:, :2], rtol=1e-10)
     pd_mc = summ.diagnostics["mc_accept"]
     assert pd_mc["value"].tolist() == full.diagnostics["mc_accept"]["value"].tolist()
+
+
+def test_outputs_too_large_for_device_memory_is_an_error_not_a_crash():
+    """the reference returns every draw; a run whose stored draws cannot fit in HBM is refused
+    up front with advice, nothing is allocated."""
+    df = drj.define_params("name", "mu", "min", -2, "max", 2, "name", "gamma", "min", 30, "max", 30)
+    drj.use_builtin("doublewell")
+    with pytest.raises(drj.DrjacobyError) as e:
+        drj.run_mcmc({"x": [-1.0]}, df, loglike="loglike", logprior="logprior", burnin=10, samples=5e6, rungs=32, chains=4096,
+                     silent=True, as_frames=False)
+    assert e.value.code == 14 and "device memory" in str(e.value)
+
+
+def test_two_sessions_interleaved_on_one_device():
+    """Sessions own their stream and buffers: interleaving two of them changes nothing."""
+    from drjacoby_b200 import Model, RunSpec, Session
+    x = np.random.default_rng(8).normal(3, 2, 60)
+    def spec(seed):
+        return RunSpec(theta_min=[-10, 0], theta_max=[10, np.inf], theta_init=[[1.0, 1.0], [2.0, 2.0], [0.0, 3.0]], burnin=40,
+                       samples=60, beta_raised=np.linspace(0, 1, 4), seed=seed, data=[x])
+    m = Model(builtin="example")
+    a, b = Session(m, spec(1)), Session(m, spec(2))
+    for n in (7, 30, 1, 100):
+        a.advance(n); b.advance(n)
+    oa, ob = a.download(), b.download()
+    a.close(); b.close()
+    ra, rb = drj.run_raw(m, spec(1)), drj.run_raw(m, spec(2))
+    for k in ra:
+        if k != "t_diff":
+            assert np.array_equal(oa[k], ra[k]) and np.array_equal(ob[k], rb[k]), k
+    assert not np.array_equal(oa["theta_sampling"], ob["theta_sampling"])
