@@ -12,7 +12,8 @@
 // Metropolis-coupling pass is a shared-memory pass; every chain x rung advances in lock-step, so a
 // per-datum likelihood is evaluated CTA-wide: data tiles are staged ONCE per CTA into shared
 // memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier, double buffered) and every thread
-// walks the tile with broadcast LDS, accumulating its own sum in index order.  Samples go to
+// walks the tile with broadcast LDS, accumulating its own sum (8 interleaved partial sums, assigned by
+// global datum index).  Samples go to
 // [iteration][particle] rings (coalesced) and are transposed on the device into the reference's
 // per-chain layout.
 //
