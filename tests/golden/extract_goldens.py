@@ -37,6 +37,11 @@ mc_rates = [float(v) for v in re.findall(r"acceptance rate: ([0-9.]+)%", mc)]
 dw = text_of("checks_double_well.html")
 dw_rates = [float(v) for v in re.findall(r"acceptance rate: ([0-9.]+)%", dw)]
 
+gm = text_of("getting_model_fits.html")
+gm_rates = [float(v) for v in re.findall(r"acceptance rate: ([0-9.]+)%", gm)]
+pl = text_of("parallel.html")
+pl_rates = [float(v) for v in re.findall(r"acceptance rate: ([0-9.]+)%", pl)]
+
 out = {
     "source": "mrc-ide/drjacoby docs/articles (pkgdown build 2024-06-26), package version 1.5.4",
     "example": {
@@ -52,6 +57,16 @@ out = {
         "where": "docs/articles/metropolis_coupling.html:284,287; setup vignettes/metropolis_coupling.Rmd:21,52-61,70-107",
         "setup": "set.seed(1); x = rnorm(100, 10, 1); init (5,5,0); nine runs 1 rung 1e3+1e4; then rungs=20, 1e3+1e4",
         "acceptance_pct_all_runs": mc_rates,
+    },
+    "getting_model_fits": {
+        "where": "docs/articles/getting_model_fits.html:247-266; setup vignettes/getting_model_fits.Rmd:21,61-63,72-116",
+        "setup": "set.seed(1); population_data; N_0 in [1,100], r in [1,2], N_max in [50,200], no init; logistic map + dpois (R closures); 3 chains, 1e3+1e4",
+        "acceptance_pct_all_runs": gm_rates,
+    },
+    "parallel": {
+        "where": "docs/articles/parallel.html:181-192; setup vignettes/parallel.Rmd:21,36-66",
+        "setup": "set.seed(1); x = rnorm(10); mu in [-10,10], init 0; sum dnorm(x, mu, 1); 2 chains, 1e3+1e3",
+        "acceptance_pct_all_runs": pl_rates,
     },
     "double_well": {
         "where": "docs/articles/checks_double_well.html:203,206; setup vignettes/checks_double_well.Rmd:18,46-65,91-101",

@@ -332,3 +332,29 @@ def test_two_sessions_interleaved_on_one_device():
         if k != "t_diff":
             assert np.array_equal(oa[k], ra[k]) and np.array_equal(ob[k], rb[k]), k
     assert not np.array_equal(oa["theta_sampling"], ob["theta_sampling"])
+
+
+def test_getting_model_fits_vignette_on_the_gpu():
+    """docs/articles/getting_model_fits.html:247-266 (K3's model): six printed acceptance rates, from the GPU."""
+    from helpers import POPULATION
+    rs = drj.RStream(1)
+    df = drj.define_params("name", "N_0", "min", 1, "max", 100, "name", "r", "min", 1, "max", 2, "name", "N_max", "min", 50, "max", 200)
+    drj.use_builtin("logistic")
+    res = drj.run_mcmc(data={"pop": POPULATION["pop"], "time": POPULATION["time"]}, df_params=df, misc={"output_type": 1},
+                       loglike="loglike", logprior="logprior", burnin=1e3, samples=1e4, chains=3, rng="r", seed=rs, silent=True)
+    got = [v for pair in rates_of(res, 1000, 10000, 3) for v in pair]
+    assert got == GOLD["getting_model_fits"]["acceptance_pct_all_runs"]
+    # the fitted curve plateaus near the carrying capacity the data suggest
+    assert 90 < res.output[res.output["phase"] == "sampling"]["N_max"].median() < 115
+
+
+def test_parallel_vignette_on_the_gpu():
+    """docs/articles/parallel.html:181-192."""
+    rs = drj.RStream(1)
+    data = {"x": rs.rnorm(10)}
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "init", 0)
+    drj.use_builtin("normal_mu")
+    res = drj.run_mcmc(data=data, df_params=df, loglike="loglike", logprior="logprior", burnin=1e3, samples=1e3, chains=2, rng="r",
+                       seed=rs, silent=True)
+    got = [v for pair in rates_of(res, 1000, 1000, 1) for v in pair]
+    assert got == GOLD["parallel"]["acceptance_pct_all_runs"]

@@ -147,3 +147,32 @@ def test_replay_indexing_equals_sequential_stream(oracle):
     rep = oracle.run("example", [x], [], tmin, tmax, init, burnin=50, samples=60, beta_raised=beta, rng_mode="replay", replay=u)
     for name in ("theta_sampling", "loglike_sampling", "accept_sampling", "mc_accept_sampling", "theta_burnin"):
         assert np.array_equal(getattr(seq, name), getattr(rep, name)), name
+
+
+def test_getting_model_fits_vignette(oracle):
+    """docs/articles/getting_model_fits.html:247-266: the logistic-growth model (K3's model: 100-step map +
+    dpois, three [a,b] parameters, default inits) -- all six printed acceptance rates."""
+    from helpers import POPULATION
+    g = GOLD["getting_model_fits"]["acceptance_pct_all_runs"]
+    rs = oracle.RStream(1)
+    tmin, tmax = np.array([1.0, 1.0, 50.0]), np.array([100.0, 2.0, 200.0])
+    init = default_init(rs, tmin, tmax, 3)
+    r = oracle.run("logistic", [POPULATION["pop"], POPULATION["time"]], [], tmin, tmax, init, burnin=1000, samples=10000,
+                   rng_mode="rmt", rstream=rs)
+    got = []
+    for c in range(3):
+        got += [printed_rate(r.accept_burnin[c, 0], 1000, 3), printed_rate(r.accept_sampling[c, 0], 10000, 3)]
+    assert got == g
+
+
+def test_parallel_vignette(oracle):
+    """docs/articles/parallel.html:181-192: normal mean, sd 1, mu in [-10,10] init 0, two chains."""
+    g = GOLD["parallel"]["acceptance_pct_all_runs"]
+    rs = oracle.RStream(1)
+    x = rs.rnorm(10)
+    r = oracle.run("normal_mu", [x], [], np.array([-10.0]), np.array([10.0]), np.zeros((2, 1)), burnin=1000, samples=1000,
+                   rng_mode="rmt", rstream=rs)
+    got = []
+    for c in range(2):
+        got += [printed_rate(r.accept_burnin[c, 0], 1000, 1), printed_rate(r.accept_sampling[c, 0], 1000, 1)]
+    assert got == g
