@@ -154,21 +154,27 @@ def target_regime_sweep(drj, device, chain_offset, fp64_peak):
 
 
 def ess_sweep(drj, device):
-    """ESS/s (coda definition, min over parameters, summed over chains) on the K1 model: n=100, 1 rung,
-    burnin 1e3 + samples 1e4, 1024 chains; ESS is evaluated on 64 chains and scaled."""
+    """ESS/s, SURVEY 8(d)(iii): coda::effectiveSize of the cold-rung sampling draws of ALL chains
+    concatenated (R/main.R:521-526), min over the free parameters, divided by the wall time of the run.
+    K1 model (n = 100, 1 rung, burnin 1e3 + samples 1e4) on 1024 chains; the autocovariances come from the
+    on-device summary (drj_session_summary), so the 2e7 draws are not moved."""
     from drjacoby_b200 import diagnostics as dg
     x = synth_data(100)
-    chains = 1024
+    chains, samples = 1024, 10000
     spec = drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=default_init(chains, 5),
-                       burnin=1000, samples=10000, rng_mode="philox", seed=3, device=device, data=[x])
+                       burnin=1000, samples=samples, rng_mode="philox", seed=3, device=device, data=[x])
     t0 = time.perf_counter()
-    out = drj.run_raw(drj.Model(builtin="example"), spec)
+    s = drj.Session(drj.Model(builtin="example"), spec)
+    s.advance(spec.T)
+    sm = s.summary()
     dt = time.perf_counter() - t0
-    th = out["theta_sampling"][:, 0]  # [chains, samples, d]
-    pick = np.linspace(0, chains - 1, 64).astype(int)
-    ess = np.array([[dg.ess(th[c, :, k]) for k in range(2)] for c in pick]).min(axis=1)
-    return {"workload": "K1 model n=100, 1024 chains x 1 rung, 1e3+1e4 iterations", "wall_s": dt,
-            "ess_per_chain_min_param": float(ess.mean()), "value": float(ess.mean() * chains / dt), "unit": "ESS/s"}
+    s.close()
+    n_tot = chains * samples
+    ess = [dg.ess_from_autocov(sm["autocov_sum"][k], n_tot) for k in range(2)]
+    rhat = [dg.gelman_rubin_from_moments(sm["chain_mean"][:, k], sm["chain_var"][:, k], samples) for k in range(2)]
+    return {"workload": "K1 model n=100, 1024 chains x 1 rung, 1e3+1e4 iterations", "wall_s": dt, "ess_mu_sigma": ess, "rhat_mu_sigma": rhat,
+            "draws": n_tot, "value": float(min(ess) / dt), "unit": "ESS/s",
+            "definition": "coda::effectiveSize of the concatenated cold-rung sampling draws, min over parameters, / wall"}
 
 
 def run_ours(args):
