@@ -67,7 +67,8 @@ class DrjOutput(C.Structure):
 class DrjSummary(C.Structure):
     _fields_ = [("max_lag", C.c_int32), ("reserved", C.c_int32), ("center", C.POINTER(C.c_double)),
                 ("chain_mean", C.POINTER(C.c_double)), ("chain_var", C.POINTER(C.c_double)),
-                ("autocov_sum", C.POINTER(C.c_double)), ("deviance_mean_var", C.POINTER(C.c_double))]
+                ("autocov_sum", C.POINTER(C.c_double)), ("deviance_mean_var", C.POINTER(C.c_double)),
+                ("head", C.POINTER(C.c_double)), ("tail", C.POINTER(C.c_double))]
 
 
 class DrjError(C.Structure):

@@ -392,8 +392,8 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
 def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, world, beta_raised):
     """output="summary": run the shard in a session, reduce the draws on the device, bring back only the
     summaries and counters; across ranks the per-chain moments are gathered and the autocovariance sums
-    (about the global mean) added.  Pairs of draws that straddle two ranks' shards (at most order.max per
-    boundary out of chains x samples) are not counted."""
+    (about the global mean) added, plus the lag products that straddle two ranks' shards (from each shard's
+    first / last order.max draws), so the result equals the single-GPU one."""
     sess = engine.Session(model, spec)
     try:
         nb = spec.burnin - 1
@@ -425,11 +425,20 @@ def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, worl
         else:
             parts = {"m": mean, "v": var, "dev": dev[None, :]}
             center = mean.mean(axis=0)
-        ac = sess.summary(max_lag=max_lag, center=center)["autocov_sum"]
+        second = sess.summary(max_lag=max_lag, center=center)
+        ac = second["autocov_sum"]
         if world > 1:
             t = torch.from_numpy(ac).to(devc)
             dist.all_reduce(t)
             ac = t.cpu().numpy()
+            # lag products that straddle two ranks' shards: tail of rank k x head of rank k+1
+            ends = gather_shards({"head": second["head"][None], "tail": second["tail"][None]}, chains, rank, world)
+            if rank == 0 and max_lag > 0:
+                for k in range(world - 1):
+                    tl, hd = ends["tail"][k] - center[:, None], ends["head"][k + 1] - center[:, None]   # [d, L]
+                    for lag in range(1, max_lag + 1):
+                        # x_j in the last `lag` draws of shard k pairs with x_{j+lag} among the first `lag` of shard k+1
+                        ac[:, lag] += (tl[:, max_lag - lag:] * hd[:, :lag]).sum(axis=1)
         raw = sess.download(draws=False)
         if world > 1:
             raw = gather_shards(raw, chains, rank, world)

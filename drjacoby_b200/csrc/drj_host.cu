@@ -157,6 +157,18 @@ __global__ void drj_reduce_partials(const double* __restrict__ partial, int nblo
   }
 }
 
+// the first / last L elements of the concatenated series of every parameter: out[k][i]
+__global__ void drj_series_ends(const double* __restrict__ src, long long cs, long long ts, int S, long long N, int D, int L,
+                                double* __restrict__ head, double* __restrict__ tail) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  for (int k = 0; k < D; ++k) {
+    const long long jh = i, jt = N - L + i;
+    head[(long long)k * L + i] = (jh < N) ? src[(jh / S) * cs + (jh % S) * ts + k] : 0.0;
+    tail[(long long)k * L + i] = (jt >= 0) ? src[(jt / S) * cs + (jt % S) * ts + k] : 0.0;
+  }
+}
+
 // FP64 FMA throughput probe: 8 independent dependent-chains per thread
 __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
@@ -1020,6 +1032,23 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
       SUM_TRY(cudaStreamSynchronize(s->stream));
       memcpy(sm->autocov_sum + (size_t)k * (L + 1), ac.data(), sizeof(double) * ac.size());
     }
+  }
+  if ((sm->head || sm->tail) && L > 0) {
+    double *d_head = nullptr, *d_tail = nullptr;
+    SUM_TRY(cudaMalloc(&d_head, sizeof(double) * (size_t)D * L));
+    e = cudaMalloc(&d_tail, sizeof(double) * (size_t)D * L);
+    if (e != cudaSuccess) { cudaFree(d_head); cleanup(); CUDA_TRY(e); }
+    drj_series_ends<<<(L + 127) / 128, 128, 0, s->stream>>>(th, th_cs, th_ts, S, N, D, L, d_head, d_tail);
+    s->aux_launches++;
+    std::vector<double> hh((size_t)D * L), tt((size_t)D * L);
+    e = cudaMemcpyAsync(hh.data(), d_head, sizeof(double) * hh.size(), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tt.data(), d_tail, sizeof(double) * tt.size(), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_head);
+    cudaFree(d_tail);
+    SUM_TRY(e);
+    if (sm->head) memcpy(sm->head, hh.data(), sizeof(double) * hh.size());
+    if (sm->tail) memcpy(sm->tail, tt.data(), sizeof(double) * tt.size());
   }
   SUM_TRY(cudaGetLastError());
 #undef SUM_TRY

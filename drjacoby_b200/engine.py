@@ -243,7 +243,8 @@ class Session:
         if max_lag is None:
             max_lag = min(n_tot - 1, int(np.floor(10 * np.log10(n_tot))))  # stats::ar's order.max
         out = dict(chain_mean=np.zeros((sp.chains, sp.d)), chain_var=np.zeros((sp.chains, sp.d)),
-                   autocov_sum=np.zeros((sp.d, max_lag + 1)), deviance_mean_var=np.zeros(2))
+                   autocov_sum=np.zeros((sp.d, max_lag + 1)), deviance_mean_var=np.zeros(2),
+                   head=np.zeros((sp.d, max(max_lag, 1))), tail=np.zeros((sp.d, max(max_lag, 1))))
         sm = L.DrjSummary()
         sm.max_lag = int(max_lag)
         ctr = None
@@ -252,6 +253,7 @@ class Session:
             sm.center = L.dptr(ctr)
         sm.chain_mean, sm.chain_var = L.dptr(out["chain_mean"]), L.dptr(out["chain_var"])
         sm.autocov_sum, sm.deviance_mean_var = L.dptr(out["autocov_sum"]), L.dptr(out["deviance_mean_var"])
+        sm.head, sm.tail = L.dptr(out["head"]), L.dptr(out["tail"])
         err = L.DrjError()
         rc = L.lib().drj_session_summary(self._h, C.byref(sm), C.byref(err))
         L.raise_for(rc, err, sp.d)

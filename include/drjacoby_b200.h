@@ -144,6 +144,9 @@ typedef struct drj_summary {
   double* chain_var;         /* out [chains][d] sample variance (n-1); may be NULL */
   double* autocov_sum;       /* out [d][max_lag+1]: sum_j (x_j - c)(x_{j+l} - c), chains concatenated; may be NULL */
   double* deviance_mean_var; /* out [2]: mean and sample variance of -2 loglike; may be NULL */
+  double* head;              /* out [d][max_lag]: the first max_lag draws of the concatenated series; may be NULL */
+  double* tail;              /* out [d][max_lag]: the last max_lag draws (with head: lets the caller add the lag
+                                products that straddle two shards when chains are split over GPUs); may be NULL */
 } drj_summary;
 
 typedef struct drj_error {
