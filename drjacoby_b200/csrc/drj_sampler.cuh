@@ -232,7 +232,7 @@ __device__ __forceinline__ void drj_accum_span(const typename M::Consts& k, cons
     // prefetches 8 doubles past the span; the tile buffer carries 8 doubles of slack.
     const unsigned base = drj_smem_addr(buf);
     double2 c0 = drj_lds2(base), c1 = drj_lds2(base + 16), c2 = drj_lds2(base + 32), c3 = drj_lds2(base + 48);
-#pragma unroll 2
+#pragma unroll 4
     for (int j = 0; j < n8; ++j) {
       const unsigned ad = base + 64u * (unsigned)j + 64u;
       const double2 n0 = drj_lds2(ad), n1 = drj_lds2(ad + 16), n2 = drj_lds2(ad + 32), n3 = drj_lds2(ad + 48);
