@@ -766,6 +766,10 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     const int fit = (int)std::max<long long>(1, (C + want_ctas - 1) / want_ctas);
     cpc = std::min(cpc, fit);
     cpc = std::max(cpc, std::min(max_cpc, (32 + R - 1) / R));  // but never less than one full warp
+    if (const char* e = getenv("DRJ_CHAINS_PER_CTA")) {            // tuning override
+      const int v = atoi(e);
+      if (v > 0) cpc = std::min(v, max_cpc);
+    }
   }
   s->cpc = cpc;
   s->nthreads = std::min(DRJ_NT, ((cpc * R + 31) / 32) * 32);
