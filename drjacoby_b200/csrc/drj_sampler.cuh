@@ -272,7 +272,7 @@ __device__ __forceinline__ double drj_sweep_item_inl(DrjTiles<M, true>& T, const
   const unsigned tile_bytes = DRJ_TILE * sizeof(double);
   if (T.tma) {
     // prologue: TMA engine fills both stages (the buffer is padded to whole tiles by the host)
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && ntiles > 0) {
       drj_mbar_expect_tx(&full[0], tile_bytes);
       drj_bulk_g2s(buf, g, tile_bytes, &full[0]);
       if (ntiles > 1) {

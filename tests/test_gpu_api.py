@@ -391,7 +391,7 @@ __device__ double logprior(const double* params, const DrjList& misc) { return 0
 """
 
 
-@pytest.mark.parametrize("n", [37, 5000])
+@pytest.mark.parametrize("n", [0, 37, 5000])
 def test_multi_block_datum_form_model(n):
     """A per-datum model with two likelihood blocks over two data vectors (always streamed in tiles) against the
     same model in the generic form: same acceptances, values within the 1e-10 gate."""
@@ -408,4 +408,5 @@ def test_multi_block_datum_form_model(n):
         assert np.array_equal(a.raw[k], b.raw[k]), k
     for k in ("theta_sampling", "loglike_sampling", "theta_burnin", "loglike_burnin"):
         np.testing.assert_allclose(a.raw[k], b.raw[k], rtol=1e-10, atol=1e-12)
-    assert abs(a.raw["theta_sampling"][:, 0, :, 0].mean() - data["x"].mean()) < 0.5
+    if n > 0:
+        assert abs(a.raw["theta_sampling"][:, 0, :, 0].mean() - data["x"].mean()) < 0.5

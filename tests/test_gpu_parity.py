@@ -45,6 +45,9 @@ CASES = {
     "example_rungs256": Case("example", [-10, 0], [10, np.inf], data=[normal_data(8)], beta=beta_ladder(256), chains=2,
                              burnin=5, samples=5),
     "example_one_chain": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100)], chains=1, burnin=300, samples=300),
+    # empty data vector: the likelihood is an empty sum, the chain follows the prior
+    "example_empty_data": Case("example", [-10, 0], [10, np.inf], data=[np.zeros(0)], beta=beta_ladder(2), chains=3),
+    "example_exact_empty_data": Case("example_exact", [-10, 0], [10, np.inf], data=[np.zeros(0)], chains=2),
     "example_coupling_off": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20)], beta=beta_ladder(3),
                                  chains=2, coupling_on=False),
     # data streamed through shared memory in tiles (n > 2 tiles), ragged last tile
