@@ -48,6 +48,9 @@ CASES = {
     # empty data vector: the likelihood is an empty sum, the chain follows the prior
     "example_empty_data": Case("example", [-10, 0], [10, np.inf], data=[np.zeros(0)], beta=beta_ladder(2), chains=3),
     "example_exact_empty_data": Case("example_exact", [-10, 0], [10, np.inf], data=[np.zeros(0)], chains=2),
+    # every parameter fixed (min == max): nothing to update, only the coupling pass runs
+    "doublewell_all_fixed": Case("doublewell", [0.5, 30], [0.5, 30], beta=beta_ladder(4), chains=3, burnin=10, samples=10,
+                                 save_hot_draws=True),
     "example_coupling_off": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20)], beta=beta_ladder(3),
                                  chains=2, coupling_on=False),
     # data streamed through shared memory in tiles (n > 2 tiles), ragged last tile
