@@ -311,6 +311,9 @@ def run_ours(args):
                          "traffic": traffic, "kernel": "drj_sweep_kernel<DrjModelExample, STREAM=true>",
                          "peak_source": "FP64 FMA probe (drj_fp64_peak_tflops) measured in this run; MEASURED_PEAKS.json has no FP64 figure",
                          "algorithmic_flop_per_launch": flops_per_launch, "launch_ms": launch_s * 1e3,
+                         "note": "achieved uses the ALGORITHMIC 4 flop per datum of SURVEY 8(d) (sub, mul, fma); the kernel spends 2 FP64-pipe "
+                                 "instruction slots per datum (DADD + DFMA = 3 executed flop), and the peak probe is 2 flop per slot, so frac is "
+                                 "exactly the fraction of the FP64 pipe's issue slots used by the data sweep",
                          "hbm": {"algorithmic_bytes_per_launch": 8.0 * args.n_data * D_FREE * n_cta, "peak_gbs": hbm_peak,
                                  "achieved_gbs": 8.0 * args.n_data * D_FREE * n_cta / launch_s / 1e9,
                                  "note": "every CTA streams the data once per sweep (served by L2 after the first reader); far below the HBM roof: FP64-bound"}},
