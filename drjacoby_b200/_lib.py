@@ -21,6 +21,7 @@ ERR_INIT_NEGINF, ERR_LOGLIKE_BAD, ERR_LOGPRIOR_BAD, ERR_TRANS_TYPE = 1, 2, 3, 4
 ERR_ARG, ERR_MODEL, ERR_COMPILE, ERR_CUDA, ERR_MEMORY, ERR_INTERRUPT = 10, 11, 12, 13, 14, 15
 RNG_PHILOX, RNG_REPLAY = 0, 1
 FLAG_NO_TMA, FLAG_STREAM_KERNEL, FLAG_RESIDENT_KERNEL = 1, 2, 4
+FLAG_TEAM_KERNEL, FLAG_NO_TEAM_KERNEL = 8, 16
 
 
 class DrjList(C.Structure):

@@ -194,8 +194,10 @@ struct drj_model {
   const void* init_fn = nullptr;   // built-in: __global__ function addresses
   const void* sweep_fn = nullptr;
   const void* stream_fn = nullptr; // sweep variant for data streamed through shared memory (datum-form models)
+  const void* team_init_fn = nullptr;   // cluster-per-chain variants (datum-form models)
+  const void* team_sweep_fn = nullptr;
   CUmodule module = nullptr;       // jit
-  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr;
+  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr;
   double compile_seconds = 0.0;
   int device = 0;
 };
@@ -207,13 +209,16 @@ struct BuiltinEntry {
   const void* init_fn;
   const void* sweep_fn;
   const void* stream_fn;
+  const void* team_init_fn;
+  const void* team_sweep_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
   {                                                                                      \
     NAME, __VA_ARGS__::D, __VA_ARGS__::NBLOCK, __VA_ARGS__::DATUM_FORM,                  \
         (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__, false>, \
-        DrjStreamKernel<__VA_ARGS__>::get()                                                            \
+        DrjStreamKernel<__VA_ARGS__>::get(), DrjStreamKernel<__VA_ARGS__>::team_init(),                \
+        DrjStreamKernel<__VA_ARGS__>::team_sweep()                                                     \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -244,6 +249,9 @@ struct DriverApi {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                            CUstream, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*OccupancyMaxActiveClusters)(int*, CUfunction, const CUlaunchConfig*) = nullptr;
   bool ok = false;
 };
 static DriverApi g_drv;
@@ -257,6 +265,9 @@ static bool load_driver_api() {
       {"cuModuleUnload", (void**)&g_drv.ModuleUnload},
       {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
       {"cuGetErrorString", (void**)&g_drv.GetErrorString},
+      {"cuLaunchKernelEx", (void**)&g_drv.LaunchKernelEx},
+      {"cuFuncSetAttribute", (void**)&g_drv.FuncSetAttribute},
+      {"cuOccupancyMaxActiveClusters", (void**)&g_drv.OccupancyMaxActiveClusters},
   };
   for (auto& w : want) {
     cudaDriverEntryPointQueryResult q;
@@ -375,13 +386,19 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "static_assert(DRJ_USER_MODEL::D == DRJ_D, \"model D does not match df_params\");\n"
        "static_assert(DRJ_USER_MODEL::NBLOCK == DRJ_NBLOCK, \"model NBLOCK does not match df_params$block\");\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  drj_init_body<DRJ_USER_MODEL>(a);\n"
+       "  drj_init_body<DRJ_USER_MODEL, false>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  drj_sweep_body<DRJ_USER_MODEL, false>(a);\n"
+       "  drj_sweep_body<DRJ_USER_MODEL, false, false>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_stream(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true>(a);\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true, false>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_init_team(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_init_body<DRJ_USER_MODEL, true>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_sweep_team(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, false, true>(a);\n"
        "}\n"
        "extern \"C\" __global__ void drj_user_traits(int* out) { out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0; }\n";
   return s;
@@ -390,7 +407,7 @@ static std::string make_jit_source(const drj_model_desc* desc) {
 static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
   const double t0 = wall_now();
   const std::string src = make_jit_source(desc);
-  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v1";
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v2";
   char hex[32];
   snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)fnv1a(key_text));
   const std::string path = cache_dir() + "/" + hex + ".cubin";
@@ -445,7 +462,9 @@ static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err)
   }
   if (g_drv.ModuleGetFunction(&m->init_cu, m->module, "drj_user_init") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&m->sweep_cu, m->module, "drj_user_sweep") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->stream_cu, m->module, "drj_user_sweep_stream") != CUDA_SUCCESS)
+      g_drv.ModuleGetFunction(&m->stream_cu, m->module, "drj_user_sweep_stream") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&m->team_init_cu, m->module, "drj_user_init_team") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&m->team_sweep_cu, m->module, "drj_user_sweep_team") != CUDA_SUCCESS)
     return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
   {  // does the user's model use the per-datum form?
     CUfunction traits = nullptr;
@@ -485,6 +504,7 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       drj_model* m = new drj_model();
       m->name = b.name; m->D = b.D; m->NBLOCK = b.NBLOCK; m->datum_form = b.datum_form;
       m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->stream_fn = b.stream_fn; m->device = device;
+      m->team_init_fn = b.team_init_fn; m->team_sweep_fn = b.team_sweep_fn;
       *out = m;
       return DRJ_OK;
     }
@@ -550,6 +570,9 @@ struct drj_session {
   unsigned long long* err_key = nullptr;
   int64_t sweep_launches = 0, aux_launches = 0;
   bool stream_variant = false;  // data too large for shared memory: use the streaming sweep kernel
+  bool team = false;            // few chains x long data: cluster-per-chain kernels (drj_sweep_item_team)
+  int team_ctas = 1;            // CTAs per cluster
+  bool team_ctas_forced = false;
   unsigned dyn_smem = 0;        // dynamic shared memory of the model kernels: the data tile buffer
   double t_create = 0.0;
   bool failed = false;
@@ -610,6 +633,34 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
   const drj_model* m = s->model;
   void* params[] = {(void*)&s->a};
   const bool stream = sweep && s->stream_variant;
+  if (s->team) {  // one cluster of team_ctas CTAs per chain
+    if (m->jit) {
+      CUlaunchAttribute at[1];
+      at[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+      at[0].value.clusterDim.x = (unsigned)s->team_ctas; at[0].value.clusterDim.y = 1; at[0].value.clusterDim.z = 1;
+      CUlaunchConfig lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDimX = (unsigned)s->grid; lc.gridDimY = 1; lc.gridDimZ = 1;
+      lc.blockDimX = (unsigned)s->nthreads; lc.blockDimY = 1; lc.blockDimZ = 1;
+      lc.sharedMemBytes = s->dyn_smem; lc.hStream = (CUstream)s->stream; lc.attrs = at; lc.numAttrs = 1;
+      CUresult cr = g_drv.LaunchKernelEx(&lc, sweep ? m->team_sweep_cu : m->team_init_cu, params, nullptr);
+      if (cr != CUDA_SUCCESS) {
+        const char* es = nullptr;
+        g_drv.GetErrorString(cr, &es);
+        return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernelEx: %s", es ? es : "?");
+      }
+    } else {
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)s->team_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3(s->grid); lc.blockDim = dim3(s->nthreads);
+      lc.dynamicSmemBytes = s->dyn_smem; lc.stream = s->stream; lc.attrs = at; lc.numAttrs = 1;
+      CUDA_TRY(cudaLaunchKernelExC(&lc, sweep ? m->team_sweep_fn : m->team_init_fn, params));
+    }
+    return DRJ_OK;
+  }
   if (m->jit) {
     CUresult cr = g_drv.LaunchKernel(!sweep ? m->init_cu : (stream ? m->stream_cu : m->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1, s->dyn_smem,
                                      (CUstream)s->stream, params, nullptr);
@@ -621,6 +672,58 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
   } else {
     CUDA_TRY(cudaLaunchKernel(!sweep ? m->init_fn : (stream ? m->stream_fn : m->sweep_fn), dim3(s->grid), dim3(s->nthreads),
                               params, s->dyn_smem, s->stream));
+  }
+  return DRJ_OK;
+}
+
+static int prop_sms(const drj_session* s) {
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, s->cfg.device);
+  return n;
+}
+
+// TEAM kernels: opt in to the dynamic shared memory of the tile pipeline and to clusters of 16 CTAs, then
+// shrink the cluster until the device can co-schedule at least one
+static int team_configure(drj_session* s, drj_error* err) {
+  const drj_model* m = s->model;
+  for (int which = 0; which < 2; ++which) {
+    if (m->jit) {
+      CUfunction f = which ? m->team_sweep_cu : m->team_init_cu;
+      CUresult cr = g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem);
+      if (cr == CUDA_SUCCESS) cr = g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_NON_PORTABLE_CLUSTER_SIZE_ALLOWED, 1);
+      if (cr != CUDA_SUCCESS) return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed for the cluster kernels");
+    } else {
+      const void* f = which ? m->team_sweep_fn : m->team_init_fn;
+      CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
+      CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
+  }
+  while (s->team_ctas > 1) {
+    int nclusters = 0;
+    if (m->jit) {
+      CUlaunchAttribute at[1];
+      at[0].id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+      at[0].value.clusterDim.x = (unsigned)s->team_ctas; at[0].value.clusterDim.y = 1; at[0].value.clusterDim.z = 1;
+      CUlaunchConfig lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDimX = (unsigned)s->team_ctas; lc.gridDimY = 1; lc.gridDimZ = 1;
+      lc.blockDimX = (unsigned)s->nthreads; lc.blockDimY = 1; lc.blockDimZ = 1;
+      lc.sharedMemBytes = s->dyn_smem; lc.attrs = at; lc.numAttrs = 1;
+      if (g_drv.OccupancyMaxActiveClusters(&nclusters, m->team_sweep_cu, &lc) != CUDA_SUCCESS) nclusters = 0;
+    } else {
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)s->team_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cudaLaunchConfig_t lc;
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3(s->team_ctas); lc.blockDim = dim3(s->nthreads);
+      lc.dynamicSmemBytes = s->dyn_smem; lc.attrs = at; lc.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, m->team_sweep_fn, &lc) != cudaSuccess) { cudaGetLastError(); nclusters = 0; }
+    }
+    // all chains' clusters resident at once (a 16-CTA cluster needs a whole GPC: at most 7-8 fit), or at
+    // least one when the size was forced
+    if (nclusters >= (s->team_ctas_forced ? 1 : std::min(s->C, prop_sms(s)))) break;
+    s->team_ctas /= 2;
   }
   return DRJ_OK;
 }
@@ -808,6 +911,36 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     if (cfg->flags & DRJ_FLAG_RESIDENT_KERNEL) s->stream_variant = false;
   }
 
+  // few chains over a long data item -> one thread-block cluster per chain, the sweep divided over the
+  // cluster's threads (drj_sweep_item_team).  With P = chains x rungs threads the one-thread-per-particle
+  // kernels need ~5 cycles per datum per sweep whatever P is, until P fills the machine (~75k threads).
+  int team_stages = 3;  // x 64 KB tiles
+  {
+    long long longest = 0;
+    if (data) for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
+    const bool can = model->datum_form && data && R <= DRJ_TEAM_MAXR &&
+                     (model->jit ? (model->team_sweep_cu != nullptr && g_drv.LaunchKernelEx != nullptr) : model->team_sweep_fn != nullptr);
+    bool want = longest > 2LL * DRJ_TILE && P <= 4096;  // measured cross-over, tools/team_bench.py
+    if (cfg->flags & DRJ_FLAG_TEAM_KERNEL) want = true;
+    if (cfg->flags & DRJ_FLAG_NO_TEAM_KERNEL) want = false;
+    if (const char* e = getenv("DRJ_TEAM")) want = (e[0] == '1') ? true : (e[0] == '0' ? false : want);
+    if (can && want) {
+      s->team = true;
+      s->stream_variant = false;
+      const long long ntiles = std::max<long long>(1, (longest + DRJ_TEAM_TILE - 1) / DRJ_TEAM_TILE);
+      int K = 1;  // upper bound; team_configure() shrinks it until all chains' clusters are co-resident
+      while (K * 2 <= DRJ_TEAM_VRANKS && (long long)K * 2 * C <= prop.multiProcessorCount && K * 2 <= ntiles) K *= 2;
+      if (const char* e = getenv("DRJ_TEAM_CTAS")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) { K = v; s->team_ctas_forced = true; }
+      }
+      if (const char* e = getenv("DRJ_TEAM_STAGES")) team_stages = std::max(2, std::min(3, atoi(e)));
+      s->team_ctas = K;
+      s->cpc = DRJ_NT / R;  // slots per rung in a CTA
+      s->nthreads = DRJ_NT;
+    }
+  }
+
   // dynamic shared memory = the data tile buffer of datum-form models: the longest item if every item
   // stays resident (<= 2 tiles), else two tiles; + 8 doubles of slack for the pipelined prefetch
   if (model->datum_form && data) {
@@ -817,6 +950,12 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     const bool resident = model->NBLOCK == 1 && longest <= 2 * DRJ_TILE;
     const long long doubles = (resident ? ((longest + 1) & ~1LL) : 2LL * DRJ_TILE) + 8;
     s->dyn_smem = (unsigned)(doubles * sizeof(double));
+    if (s->team) {
+      s->dyn_smem = (unsigned)(((long long)team_stages * DRJ_TEAM_TILE + 8) * sizeof(double));
+      int rc = team_configure(s, err);
+      if (rc) return rc;
+      s->grid = C * s->team_ctas;
+    }
   }
 
   // ---- uploads
@@ -831,11 +970,11 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     // update phase is long compared with the walk (measured: K4 +6 %, the 2-parameter n = 100 sweep -6 %).
     int d_free_n = 0;
     for (int i = 0; i < D; ++i) d_free_n += cfg->skip_param[i] ? 0 : 1;
-    a.warp_local = (32 % R == 0 && !streamed && !s->stream_variant && 6 * d_free_n > R - 1) ? 1 : 0;
-    if (const char* e = getenv("DRJ_WARP_LOCAL")) if (e[0] == '1' && 32 % R == 0 && !streamed && !s->stream_variant) a.warp_local = 1;
+    a.warp_local = (32 % R == 0 && !streamed && !s->stream_variant && !s->team && 6 * d_free_n > R - 1) ? 1 : 0;
+    if (const char* e = getenv("DRJ_WARP_LOCAL")) if (e[0] == '1' && 32 % R == 0 && !streamed && !s->stream_variant && !s->team) a.warp_local = 1;
     if (const char* e = getenv("DRJ_NO_WARP_LOCAL")) if (e[0] == '1') a.warp_local = 0;
   }
-  a.chains = C; a.rungs = R; a.chains_per_cta = cpc; a.coupling_on = cfg->coupling_on ? 1 : 0;
+  a.chains = C; a.rungs = R; a.chains_per_cta = s->cpc; a.team_ctas = s->team_ctas; a.team_stages = team_stages; a.coupling_on = cfg->coupling_on ? 1 : 0;
   a.save_hot_draws = cfg->save_hot_draws ? 1 : 0; a.store_pt = cfg->store_pt ? 1 : 0;
   a.rng_mode = cfg->rng_mode; a.d_free = s->d_free;
   a.use_tma = (cfg->flags & DRJ_FLAG_NO_TMA) ? 0 : 1;

@@ -55,6 +55,8 @@ struct DrjKernelArgs {
   int d_free;
   int use_tma;
   int warp_local;      // rungs divide 32 and nothing in the loop needs a CTA barrier: chains sync per warp
+  int team_ctas;       // TEAM kernels: CTAs per cluster (one cluster per chain), 1..16
+  int team_stages;     // TEAM kernels: depth of the TMA tile pipeline (tiles resident per CTA), 2..DRJ_TEAM_MAXSTAGES
   long long chain_offset;     // global id of chain 0 (Philox counter)
   unsigned long long seed;
   double target_acceptance;
@@ -139,6 +141,29 @@ __device__ __forceinline__ double2 drj_lds2(unsigned smem_addr) {
   return v;
 }
 
+// ------------------------------------------------------------------ thread-block cluster helpers (TEAM kernels)
+__device__ __forceinline__ unsigned drj_cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned drj_cluster_id_x() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+// hardware barrier over every thread of the cluster, release/acquire at cluster scope
+__device__ __forceinline__ void drj_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store into the shared memory of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void drj_st_cluster(double* local_smem_ptr, unsigned rank, double v) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(drj_smem_addr(local_smem_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ model traits helpers
 // A model is a struct with
 //   static constexpr int D, NBLOCK;  static constexpr bool DATUM_FORM;
@@ -151,6 +176,7 @@ __device__ __forceinline__ double2 drj_lds2(unsigned smem_addr) {
 
 template <class M, bool DF = M::DATUM_FORM>
 struct DrjTiles {  // no tiles for generic models
+  template <bool TEAM>
   __device__ __forceinline__ void init(const DrjKernelArgs&) {}
 };
 
@@ -165,29 +191,50 @@ template <class M>
 __device__ __forceinline__ double* drj_tile_buf() {
   return drj_dyn_smem;
 }
+#define DRJ_TEAM_TILE 8192     // TEAM kernels: doubles per data tile (64 KB); the per-tile hand-shake (mbarrier wait,
+                               // CTA barrier, refill) is a ~700-cycle dependent chain, 16 KB tiles left it dominant
+#define DRJ_TEAM_MAXSTAGES 12  // TEAM kernels: at most this many tiles in flight per CTA
+#define DRJ_TEAM_VRANKS 16     // TEAM kernels: canonical number of partial sums a data item is split into
+#define DRJ_TEAM_MAXR 32       // TEAM kernels: at most this many rungs
 template <class M>
 __device__ __forceinline__ unsigned long long* drj_tile_bars() {
-  __shared__ __align__(8) unsigned long long s_full[2];
+  __shared__ __align__(8) unsigned long long s_full[DRJ_TEAM_MAXSTAGES];
   return s_full;
+}
+// TEAM kernels: per-thread partials of the CTA reduction, and the all-gathered partial sums
+// [parity][virtual rank][rung] every CTA of the cluster receives from its peers
+template <class M>
+__device__ __forceinline__ double* drj_team_red() {
+  __shared__ double s_red[DRJ_NT];
+  return s_red;
+}
+template <class M>
+__device__ __forceinline__ double* drj_team_part() {
+  __shared__ double s_part[2 * DRJ_TEAM_VRANKS * DRJ_TEAM_MAXR];
+  return s_part;
 }
 
 template <class M>
 struct DrjTiles<M, true> {
   unsigned ph0, ph1;           // phase parity of each stage
+  unsigned team_ph;            // TEAM: phase parity bit of every stage
+  unsigned team_pb;            // TEAM: which half of the all-gather buffer the next sweep uses
   bool resident;               // whole item lives in the tile buffer for the life of the kernel
   bool tma;
+  template <bool TEAM>
   __device__ __forceinline__ void init(const DrjKernelArgs& a) {
     double* s_buf = drj_tile_buf<M>();
     unsigned long long* full = drj_tile_bars<M>();
     ph0 = ph1 = 0;
+    team_ph = 0; team_pb = 0;
     tma = a.use_tma != 0;
     // single-item models keep the data resident when it fits the two tiles
     const int item = M::datum_item(1);
     const long long n = a.data.len(item);
-    resident = (M::NBLOCK == 1) && (n <= 2 * DRJ_TILE);
+    resident = !TEAM && (M::NBLOCK == 1) && (n <= 2 * DRJ_TILE);
     if (threadIdx.x == 0) {
-      drj_mbar_init(&full[0], 1);
-      drj_mbar_init(&full[1], 1);
+      const int nbar = TEAM ? a.team_stages : 2;
+      for (int q = 0; q < nbar; ++q) drj_mbar_init(&full[q], 1);
       drj_mbar_fence_init();
     }
     if (resident) {
@@ -316,19 +363,140 @@ __device__ __noinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typena
   return drj_sweep_item_inl<M>(T, k, g, n);
 }
 
+// ------------------------------------------------------------------ TEAM sweep (few chains x long data)
+// One thread per (chain, rung) cannot use the machine when a run has few chains: the reference's usual
+// shape is 1-10 chains over a long data vector.  The TEAM kernels give every chain a whole thread-block
+// CLUSTER: all threads of all CTAs of the cluster hold a replica of the chain's particle states (thread
+// tid = slot * R + rung replicates rung `rung`; the update arithmetic is deterministic, so the replicas
+// stay bit-identical without communication), and only the data sweep is divided: the tiles of the item
+// (DRJ_TEAM_TILE = 8192 doubles) are dealt round-robin to DRJ_TEAM_VRANKS (16) "virtual ranks", CTA c of a K-CTA cluster streams the
+// virtual ranks c, c+K, ... through an NS-deep TMA pipeline, inside a tile slot s handles the 16-byte
+// pairs s, s+S, ... (S = 256 / R slots per rung) -- lanes of one rung-group read consecutive pairs,
+// lanes of one slot broadcast -- and the per-thread partial sums are combined by a fixed tree over the
+// slots (shared memory), written to EVERY CTA of the cluster through distributed shared memory, and
+// after one hardware cluster barrier summed in virtual-rank order by every thread.  The association
+// depends only on (R, n): the result is bitwise independent of the cluster size K and of how chains are
+// sharded over GPUs.  HBM / L2 traffic is one pass over the item per chain per sweep.
 template <class M>
+__device__ __forceinline__ void drj_team_accum(const typename M::Consts& k, const double* __restrict__ buf, int cnt,
+                                               int slot, int S, DrjAcc& A) {
+  // (plain loads: pinning the next group's loads ahead of the arithmetic, as drj_accum_span does, measured
+  // 10-35 % SLOWER here -- tools/team_bench.py, round 1)
+  const double2* __restrict__ b2 = reinterpret_cast<const double2*>(buf);
+  const int np = cnt >> 1;  // whole 16-byte pairs
+  int q = slot;
+  for (; q + 3 * S < np; q += 4 * S) {
+    const double2 v0 = b2[q], v1 = b2[q + S], v2 = b2[q + 2 * S], v3 = b2[q + 3 * S];
+    A.a[0] = M::datum(k, v0.x, A.a[0]);
+    A.a[1] = M::datum(k, v0.y, A.a[1]);
+    A.a[2] = M::datum(k, v1.x, A.a[2]);
+    A.a[3] = M::datum(k, v1.y, A.a[3]);
+    A.a[4] = M::datum(k, v2.x, A.a[4]);
+    A.a[5] = M::datum(k, v2.y, A.a[5]);
+    A.a[6] = M::datum(k, v3.x, A.a[6]);
+    A.a[7] = M::datum(k, v3.y, A.a[7]);
+  }
+  for (; q < np; q += S) {
+    const double2 v = b2[q];
+    A.a[0] = M::datum(k, v.x, A.a[0]);
+    A.a[1] = M::datum(k, v.y, A.a[1]);
+  }
+  if ((cnt & 1) && slot == np % S) A.a[2] = M::datum(k, buf[cnt - 1], A.a[2]);
+}
+
+// Must be called by every thread of every CTA of the cluster (uniform control flow).  Inlined: the
+// pipeline state (phase bits) stays in registers; the TEAM kernels run one CTA per SM and may use the
+// whole register file.
+template <class M>
+__device__ __forceinline__ double drj_sweep_item_team(DrjTiles<M, true>& T, const DrjKernelArgs& a,
+                                                      const typename M::Consts& k, const double* __restrict__ g,
+                                                      long long n) {
+  double* const buf = drj_tile_buf<M>();
+  unsigned long long* const full = drj_tile_bars<M>();
+  double* const s_red = drj_team_red<M>();
+  double* const s_part = drj_team_part<M>() + T.team_pb * (DRJ_TEAM_VRANKS * DRJ_TEAM_MAXR);
+  T.team_pb ^= 1u;  // the peers may still be reading the other half (one cluster barrier per sweep)
+  const int R = a.rungs, S = a.chains_per_cta, K = a.team_ctas, NS = a.team_stages;
+  const int tid = threadIdx.x;
+  const int slot = tid / R, r = tid - slot * R;
+  const int crank = (int)drj_cluster_ctarank();
+  const int ntiles = (int)((n + DRJ_TEAM_TILE - 1) / DRJ_TEAM_TILE);
+  const int last_cnt = (int)(n - (long long)(ntiles - 1) * DRJ_TEAM_TILE);  // data points in the last tile
+
+  // producer cursor (thread 0): the next tile to request, in the order this CTA consumes them.  The
+  // copy is exactly the tile's data rounded up to 16 bytes (items are padded to even lengths).
+  int pv = crank, pt = crank, pstage = 0;
+  auto produce = [&]() {
+    while (pv < DRJ_TEAM_VRANKS && pt >= ntiles) { pv += K; pt = pv; }
+    if (pv >= DRJ_TEAM_VRANKS) return;
+    const int c = (pt == ntiles - 1) ? last_cnt : DRJ_TEAM_TILE;
+    const unsigned bytes = (unsigned)((c + 1) & ~1) * (unsigned)sizeof(double);
+    drj_mbar_expect_tx(&full[pstage], bytes);
+    drj_bulk_g2s(buf + pstage * DRJ_TEAM_TILE, g + (long long)pt * DRJ_TEAM_TILE, bytes, &full[pstage]);
+    pt += DRJ_TEAM_VRANKS;
+    pstage = (pstage + 1 == NS) ? 0 : pstage + 1;
+  };
+  if (T.tma && tid == 0)
+    for (int q = 0; q < NS; ++q) produce();
+
+  int stage = 0;
+  unsigned ph = T.team_ph;
+  for (int v = crank; v < DRJ_TEAM_VRANKS && v < ntiles; v += K) {
+    DrjAcc A;
+    A.zero();
+    for (int kt = v; kt < ntiles; kt += DRJ_TEAM_VRANKS) {
+      const int cnt = (kt == ntiles - 1) ? last_cnt : DRJ_TEAM_TILE;
+      if (T.tma) {
+        drj_mbar_wait(&full[stage], (ph >> stage) & 1u);
+        ph ^= 1u << stage;
+        if (slot < S) drj_team_accum<M>(k, buf + stage * DRJ_TEAM_TILE, cnt, slot, S, A);
+        __syncthreads();  // everyone is done with this stage before the engine refills it
+        if (tid == 0) produce();
+        stage = (stage + 1 == NS) ? 0 : stage + 1;
+      } else {
+        __syncthreads();
+        for (int j = tid; j < cnt; j += blockDim.x) buf[j] = g[(long long)kt * DRJ_TEAM_TILE + j];
+        __syncthreads();
+        if (slot < S) drj_team_accum<M>(k, buf, cnt, slot, S, A);
+      }
+    }
+    // fixed tree over the S slots of every rung
+    s_red[tid] = (slot < S) ? A.total() : 0.0;
+    __syncthreads();
+    for (int m = S; m > 1;) {
+      const int half = (m + 1) >> 1;
+      if (slot < m - half) s_red[tid] += s_red[tid + half * R];
+      __syncthreads();
+      m = half;
+    }
+    if (tid < R) {
+      const double part = s_red[tid];
+      for (int c = 0; c < K; ++c) drj_st_cluster(&s_part[v * DRJ_TEAM_MAXR + tid], (unsigned)c, part);
+    }
+  }
+  T.team_ph = ph;
+  drj_cluster_sync();
+  const int nv = ntiles < DRJ_TEAM_VRANKS ? ntiles : DRJ_TEAM_VRANKS;
+  double tot = 0.0;
+  for (int v = 0; v < nv; ++v) tot += s_part[v * DRJ_TEAM_MAXR + r];
+  return tot;
+}
+
+template <class M, bool TEAM>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const DrjKernelArgs& a,
                                                    const double* theta, int block) {
   typename M::Consts k;
   const bool fast = M::prepare(theta, a.misc, block, k);
   const int item = M::datum_item(block);
   const long long n = a.data.len(item);
-  const double acc = drj_sweep_item<M>(T, k, a.data.item(item), n);  // uniform: all threads sweep
+  double acc;  // uniform: all threads sweep
+  if constexpr (TEAM) acc = drj_sweep_item_team<M>(T, a, k, a.data.item(item), n);
+  else acc = drj_sweep_item<M>(T, k, a.data.item(item), n);
   if (fast) return M::finish(k, acc, n);
   return M::loglike(theta, a.data, a.misc, block);  // degenerate theta: exact serial evaluation
 }
 
-template <class M>
+template <class M, bool TEAM>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, false>&, const DrjKernelArgs& a,
                                                    const double* theta, int block) {
   return M::loglike(theta, a.data, a.misc, block);
@@ -396,21 +564,23 @@ __device__ __forceinline__ void drj_store_state(const DrjKernelArgs& a, const Dr
 // ------------------------------------------------------------------ init kernel body
 // Particle::init + theta_to_phi + init_like for every (chain, rung); writes state and row 0 of the
 // burn-in outputs (main.cpp:128-137).
-template <class M>
+// TEAM: one cluster per chain, every thread a replica of rung (tid mod R); the replica in slot 0 of CTA 0
+// of the cluster (`active`) is the one that writes to HBM.
+template <class M, bool TEAM>
 __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
   const int R = a.rungs;
   const int tid = threadIdx.x;
   const int lc = tid / R, r = tid - lc * R;
-  const long long chain = (long long)blockIdx.x * a.chains_per_cta + lc;
-  const bool active = (lc < a.chains_per_cta) && (chain < a.chains);
-  const long long cc = active ? chain : 0;  // inactive threads shadow chain 0 (uniform control flow)
+  const long long chain = TEAM ? (long long)drj_cluster_id_x() : (long long)blockIdx.x * a.chains_per_cta + lc;
+  const bool active = TEAM ? (lc == 0 && drj_cluster_ctarank() == 0u) : ((lc < a.chains_per_cta) && (chain < a.chains));
+  const long long cc = (TEAM || active) ? chain : 0;  // inactive threads shadow chain 0 (uniform control flow)
   const long long p = cc * R + r;
   const long long P = a.P;
 
   DrjTiles<M> T;
-  T.init(a);
+  T.template init<TEAM>(a);
 
   DrjState<M> s;
   int err = 0;
@@ -443,7 +613,7 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
         if ((seen >> (b - 1)) & 1ULL) continue;
         seen |= 1ULL << (b - 1);
       }
-      s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
+      s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, TEAM>(T, a, s.theta, b);
     }
   s.ll = 0.0;
 #pragma unroll UB
@@ -498,19 +668,25 @@ __device__ __forceinline__ int drj_sync_or(bool warp_local, int pred) {
 // register file for its software pipeline (with the state live ptxas squeezes the loop into the ~48
 // remaining registers and the LDS->DFMA distance collapses; profiles/README.md).  Costs ~0.3 KB of
 // HBM traffic per thread per sweep of n >= 4097 data points.
-template <class M, bool STREAM>
+//
+// TEAM = one thread-block cluster per chain (few chains x long data, see drj_sweep_item_team): every
+// thread is a replica of rung (tid mod R) of the cluster's chain and runs the whole update redundantly;
+// `valid` = the thread holds a real particle, `active` = it is the replica that writes to HBM.
+template <class M, bool STREAM, bool TEAM>
 __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
+  static_assert(!(STREAM && TEAM), "TEAM replicas keep their state in registers");
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
   const int R = a.rungs;
   const int tid = threadIdx.x;
   const int lc = tid / R, r = tid - lc * R;
-  const long long chain = (long long)blockIdx.x * a.chains_per_cta + lc;
-  const bool active = (lc < a.chains_per_cta) && (chain < a.chains);
-  const long long cc = active ? chain : 0;
+  const long long chain = TEAM ? (long long)drj_cluster_id_x() : (long long)blockIdx.x * a.chains_per_cta + lc;
+  const bool active = TEAM ? (lc == 0 && drj_cluster_ctarank() == 0u) : ((lc < a.chains_per_cta) && (chain < a.chains));
+  const bool valid = TEAM || active;
+  const long long cc = valid ? chain : 0;
   const long long p = cc * R + r;
   const long long P = a.P;
-  const int base = lc * R;  // first thread of this chain in the CTA
+  const int base = TEAM ? 0 : lc * R;  // first thread of this chain in the CTA (TEAM: slot 0 serves all replicas)
 
   __shared__ double s_tmin[D], s_tmax[D];
   __shared__ int s_trans[D], s_free[D];
@@ -528,7 +704,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   s_mc[tid] = 0;
 
   DrjTiles<M> T;
-  T.init(a);
+  T.template init<TEAM>(a);
   __syncthreads();
 
   // ---- load state into registers
@@ -542,7 +718,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   const unsigned gchain_hi = (unsigned)((unsigned long long)(a.chain_offset + cc) >> 32);
   const unsigned k0 = (unsigned)a.seed, k1 = (unsigned)(a.seed >> 32);
   const bool do_couple = a.coupling_on && R > 1;
-  const bool wl = a.warp_local != 0;
+  const bool wl = !TEAM && a.warp_local != 0;
   const int lane = tid & 31;
 
   for (int it = 0; it < a.n_iter; ++it) {
@@ -596,7 +772,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           drj_load_state<M>(a, s, p);
           s.llb_p[B == 1 ? 0 : b - 1] = fast ? M::finish(k, acc, n) : M::loglike(s.theta, a.data, a.misc, b);
         } else {
-          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M>(T, a, s.theta, b);
+          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, TEAM>(T, a, s.theta, b);
         }
       }
       double ll_p = 0.0;
@@ -604,10 +780,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       for (int b = 0; b < B; ++b) ll_p += s.llb_p[b];  // sequential, index order (misc.h:20-27)
       const double lp_p = M::logprior(s.theta, a.misc);
       // NaN / +Inf guard (Particle.h:121-128)
-      if (err == 0 && active) {
+      if (err == 0 && valid) {
         if (isnan(ll_p) || ll_p == DRJ_INF) err = DRJ_ERR_LOGLIKE_BAD;
         else if (isnan(lp_p) || lp_p == DRJ_INF) err = DRJ_ERR_LOGPRIOR_BAD;
-        if (err) drj_report(a, err, it, chain, r, i, p, s.theta, D);
+        if (err && active) drj_report(a, err, it, chain, r, i, p, s.theta, D);
       }
       // Metropolis-Hastings (Particle.h:131-139)
       double MH;
@@ -673,8 +849,9 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       // The replica that is swapped upwards is carried along.
       const int wb = wl ? ((tid & ~31) + lane * R) : tid * R;
       const int wlc = wb / R;
-      const bool walker = (wl ? (lane < 32 / R) : true) && wlc < a.chains_per_cta &&
-                          (long long)blockIdx.x * a.chains_per_cta + wlc < a.chains;
+      const bool walker = TEAM ? (tid == 0)
+                               : ((wl ? (lane < 32 / R) : true) && wlc < a.chains_per_cta &&
+                                  (long long)blockIdx.x * a.chains_per_cta + wlc < a.chains);
       if (walker) {
         int cur_src = 0;
         double cur_ll = s_x[wb];
@@ -698,7 +875,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         s_src[wb + R - 1] = (short)cur_src;
       }
       drj_sync(wl);
-      const int src = active ? (int)s_src[tid] : r;
+      const int src = TEAM ? (int)s_src[r] : (active ? (int)s_src[tid] : r);
       const int from = base + src;
       if (drj_sync_or(wl, src != r)) {
         // replica-owned state moves: theta, phi, Jacobian logs, loglike_block, loglike, logprior.
@@ -744,8 +921,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
     // ================= abort on error (Rcpp::stop in the reference) =================
     // one barrier: own error, or (seen by thread 0) an error reported by any other CTA
+    // (TEAM: the decision must be the same in every CTA of the cluster, which meet at a cluster barrier
+    // in the next sweep -- own error only, it is identical in all replicas)
     int stop = err;
-    if ((wl ? lane == 0 : tid == 0) && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
+    if (!TEAM && (wl ? lane == 0 : tid == 0) && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
     if (drj_sync_or(wl, stop)) break;
   }
   drj_sync(wl);
@@ -760,18 +939,31 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 // ------------------------------------------------------------------ kernels
 template <class M>
 __global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant__ DrjKernelArgs a) {
-  drj_init_body<M>(a);
+  drj_init_body<M, false>(a);
 }
 template <class M, bool STREAM>
 __global__ void __launch_bounds__(DRJ_NT, (STREAM ? 2 : DRJ_MINB)) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
-  drj_sweep_body<M, STREAM>(a);
+  drj_sweep_body<M, STREAM, false>(a);
 }
-// address of the streaming variant (datum-form models only)
+// cluster-per-chain variants (launched with a cluster dimension of a.team_ctas; datum-form models only)
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT, 1) drj_init_kernel_team(const __grid_constant__ DrjKernelArgs a) {
+  drj_init_body<M, true>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT, 1) drj_sweep_kernel_team(const __grid_constant__ DrjKernelArgs a) {
+  drj_sweep_body<M, false, true>(a);
+}
+// addresses of the variants that only exist for datum-form models
 template <class M, bool DF = M::DATUM_FORM>
 struct DrjStreamKernel {
   static const void* get() { return nullptr; }
+  static const void* team_init() { return nullptr; }
+  static const void* team_sweep() { return nullptr; }
 };
 template <class M>
 struct DrjStreamKernel<M, true> {
   static const void* get() { return (const void*)drj_sweep_kernel<M, true>; }
+  static const void* team_init() { return (const void*)drj_init_kernel_team<M>; }
+  static const void* team_sweep() { return (const void*)drj_sweep_kernel_team<M>; }
 };
