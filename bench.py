@@ -177,6 +177,42 @@ def ess_sweep(drj, device):
             "definition": "coda::effectiveSize of the concatenated cold-rung sampling draws, min over parameters, / wall"}
 
 
+def few_chains_sweep(drj, device, x, with_cpu):
+    """The reference's everyday shape -- a handful of chains over a long data vector (run_mcmc defaults:
+    chains = 5, R/main.R:213-216) -- where one thread per chain-rung cannot fill a GPU: every chain gets a
+    thread-block cluster and the likelihood sum is divided over it (cluster-per-chain kernels,
+    drj_sweep_item_team).  `swept_GBps` = chains x 2 sweeps x 8 n bytes per iteration / time: every cluster
+    streams the whole item through its TMA pipeline once per likelihood evaluation (from L2 when chains
+    share it).  The CPU figure is the oracle on the same shape, one chain per thread."""
+    from oracle import pyoracle as po
+    out = []
+    for chains, rungs, n, iters in ((5, 1, x.size, 200), (5, 20, min(x.size, 1_000_000), 200)):
+        xs = x[:n]
+        beta = np.linspace(0.0, 1.0, rungs) if rungs > 1 else [1.0]
+        spec = drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=default_init(chains, 79), burnin=1,
+                           samples=2 * iters + 1, beta_raised=beta, store_pt=False, rng_mode="philox", seed=2, device=device,
+                           data=[xs], iters_per_launch=iters)
+        s = drj.Session(drj.Model(builtin="example"), spec)
+        s.advance(iters)
+        ms = s.advance(iters)
+        s.close()
+        ups = chains * rungs * D_FREE * iters / (ms * 1e-3)
+        row = {"workload": f"normal model n={n}, {chains} chains x {rungs} rung(s), one GPU", "iterations": iters, "kernel_ms": ms,
+               "value": ups, "unit": UNIT, "swept_GBps": chains * D_FREE * 8.0 * n * iters / (ms * 1e-3) / 1e9,
+               "sweep_tflops": FLOP_PER_DATUM * n * ups / 1e12}
+        if with_cpu:
+            po.build()
+            threads = min(chains, os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            po.run("example", [xs], [], np.array([-10.0, 0.0]), np.array([10.0, np.inf]), default_init(chains, 79), burnin=1,
+                   samples=1, beta_raised=np.asarray(beta, dtype=np.float64), rng_mode="philox", seed=2, n_threads=threads)
+            dt = time.perf_counter() - t0
+            row["cpu_port"] = {"value": chains * rungs * D_FREE * 2 / dt, "unit": UNIT, "cores": threads,
+                               "sample": f"same shape, 1 iteration + initial likelihood in {dt:.2f} s"}
+        out.append(row)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -267,6 +303,7 @@ def run_ours(args):
         extra["small_n"] = small_n_sweep(drj, device, chain_offset)
         extra["target_regime"] = target_regime_sweep(drj, device, chain_offset, fp64_peak)
         extra["ess"] = ess_sweep(drj, device)
+        extra["few_chains"] = few_chains_sweep(drj, device, x, n_gpus == 1 and not args.no_cpu)
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu:

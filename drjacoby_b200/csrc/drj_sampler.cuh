@@ -377,16 +377,23 @@ __device__ __noinline__ double drj_sweep_item(DrjTiles<M, true>& T, const typena
 // after one hardware cluster barrier summed in virtual-rank order by every thread.  The association
 // depends only on (R, n): the result is bitwise independent of the cluster size K and of how chains are
 // sharded over GPUs.  HBM / L2 traffic is one pass over the item per chain per sweep.
+__device__ __forceinline__ int drj_team_pairs(int cnt, int slot, int S) {
+  const int np = cnt >> 1;  // whole 16-byte pairs in the tile
+  return np > slot ? (np - slot + S - 1) / S : 0;
+}
 template <class M>
 __device__ __forceinline__ void drj_team_accum(const typename M::Consts& k, const double* __restrict__ buf, int cnt,
-                                               int slot, int S, DrjAcc& A) {
+                                               int slot, int S, int mine, DrjAcc& A) {
+  // `mine` = drj_team_pairs(cnt, slot, S): the 16-byte pairs slot, slot + S, ... of this thread in the tile.
   // (plain loads: pinning the next group's loads ahead of the arithmetic, as drj_accum_span does, measured
-  // 10-35 % SLOWER here -- tools/team_bench.py, round 1)
-  const double2* __restrict__ b2 = reinterpret_cast<const double2*>(buf);
-  const int np = cnt >> 1;  // whole 16-byte pairs
-  int q = slot;
-  for (; q + 3 * S < np; q += 4 * S) {
-    const double2 v0 = b2[q], v1 = b2[q + S], v2 = b2[q + 2 * S], v3 = b2[q + 3 * S];
+  // 10-35 % SLOWER here; a counted loop the compiler can unroll is what helps -- tools/team_bench.py, round 1)
+  const int np = cnt >> 1;
+  const double2* __restrict__ pq = reinterpret_cast<const double2*>(buf) + slot;
+  const int ngroups = mine >> 2;
+#pragma unroll 4
+  for (int gi = 0; gi < ngroups; ++gi) {
+    const double2 v0 = pq[0], v1 = pq[S], v2 = pq[2 * S], v3 = pq[3 * S];
+    pq += 4 * S;
     A.a[0] = M::datum(k, v0.x, A.a[0]);
     A.a[1] = M::datum(k, v0.y, A.a[1]);
     A.a[2] = M::datum(k, v1.x, A.a[2]);
@@ -396,8 +403,9 @@ __device__ __forceinline__ void drj_team_accum(const typename M::Consts& k, cons
     A.a[6] = M::datum(k, v3.x, A.a[6]);
     A.a[7] = M::datum(k, v3.y, A.a[7]);
   }
-  for (; q < np; q += S) {
-    const double2 v = b2[q];
+  for (int j = 0; j < (mine & 3); ++j) {
+    const double2 v = pq[0];
+    pq += S;
     A.a[0] = M::datum(k, v.x, A.a[0]);
     A.a[1] = M::datum(k, v.y, A.a[1]);
   }
@@ -441,6 +449,7 @@ __device__ __forceinline__ double drj_sweep_item_team(DrjTiles<M, true>& T, cons
 
   int stage = 0;
   unsigned ph = T.team_ph;
+  const int mine_full = drj_team_pairs(DRJ_TEAM_TILE, slot, S);  // (an integer division: once per sweep, not per tile)
   for (int v = crank; v < DRJ_TEAM_VRANKS && v < ntiles; v += K) {
     DrjAcc A;
     A.zero();
@@ -449,7 +458,9 @@ __device__ __forceinline__ double drj_sweep_item_team(DrjTiles<M, true>& T, cons
       if (T.tma) {
         drj_mbar_wait(&full[stage], (ph >> stage) & 1u);
         ph ^= 1u << stage;
-        if (slot < S) drj_team_accum<M>(k, buf + stage * DRJ_TEAM_TILE, cnt, slot, S, A);
+        if (slot < S)
+          drj_team_accum<M>(k, buf + stage * DRJ_TEAM_TILE, cnt, slot, S,
+                            cnt == DRJ_TEAM_TILE ? mine_full : drj_team_pairs(cnt, slot, S), A);
         __syncthreads();  // everyone is done with this stage before the engine refills it
         if (tid == 0) produce();
         stage = (stage + 1 == NS) ? 0 : stage + 1;
@@ -457,7 +468,8 @@ __device__ __forceinline__ double drj_sweep_item_team(DrjTiles<M, true>& T, cons
         __syncthreads();
         for (int j = tid; j < cnt; j += blockDim.x) buf[j] = g[(long long)kt * DRJ_TEAM_TILE + j];
         __syncthreads();
-        if (slot < S) drj_team_accum<M>(k, buf, cnt, slot, S, A);
+        if (slot < S)
+          drj_team_accum<M>(k, buf, cnt, slot, S, cnt == DRJ_TEAM_TILE ? mine_full : drj_team_pairs(cnt, slot, S), A);
       }
     }
     // fixed tree over the S slots of every rung
