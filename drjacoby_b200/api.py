@@ -408,7 +408,7 @@ def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, worl
                     raise DrjacobyError(15, "interrupted by the progress callback")
         n_tot = chains * spec.samples
         max_lag = min(n_tot - 1, int(np.floor(10 * np.log10(n_tot))))
-        first = sess.summary(max_lag=0)
+        first = sess.summary(max_lag=0, autocov=False)
         mean, var = first["chain_mean"], first["chain_var"]
         dev = np.array([first["deviance_mean_var"][0], first["deviance_mean_var"][1], spec.chains * spec.samples], dtype=np.float64)
         if world > 1:
@@ -425,7 +425,7 @@ def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, worl
         else:
             parts = {"m": mean, "v": var, "dev": dev[None, :]}
             center = mean.mean(axis=0)
-        second = sess.summary(max_lag=max_lag, center=center)
+        second = sess.summary(max_lag=max_lag, center=center, moments=False)
         ac = second["autocov_sum"]
         if world > 1:
             t = torch.from_numpy(ac).to(devc)

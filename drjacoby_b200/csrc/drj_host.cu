@@ -103,57 +103,127 @@ __device__ __forceinline__ double drj_block_sum(double v, double* sh) {
   return t;
 }
 
-// one CTA per (chain, series): mean and sample variance (two passes over the chain's S draws)
+// one CTA per (chain, series): mean and sample variance in ONE pass over the chain's S draws, as sums of
+// d = x - x_0 and d^2 (shifted-data algorithm: the pivot is a draw of the same chain, so |mean - pivot| is a
+// few standard deviations and the cancellation in sum d^2 - (sum d)^2 / S costs a few ulp), four independent
+// loads in flight per thread
 __global__ void __launch_bounds__(256) drj_chain_moments(const double* __restrict__ src, long long cs, long long ts, long long ks,
                                                         int S, int K, double* __restrict__ mean, double* __restrict__ var) {
   __shared__ double sh[8];
   const int c = blockIdx.x, k = blockIdx.y;
   const double* x = src + (long long)c * cs + (long long)k * ks;
-  double a = 0.0;
-  for (int t = threadIdx.x; t < S; t += blockDim.x) a += x[(long long)t * ts];
-  const double m = drj_block_sum(a, sh) / (double)S;
-  double q = 0.0;
-  for (int t = threadIdx.x; t < S; t += blockDim.x) { const double d = x[(long long)t * ts] - m; q = fma(d, d, q); }
-  const double m2 = drj_block_sum(q, sh);
-  if (threadIdx.x == 0) { mean[(long long)c * K + k] = m; var[(long long)c * K + k] = S > 1 ? m2 / (double)(S - 1) : 0.0; }
+  const double pivot = x[0];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+  const int B = blockDim.x;
+  int t = threadIdx.x;
+  for (; t + 3 * B < S; t += 4 * B) {
+    const double d0 = x[(long long)t * ts] - pivot, d1 = x[(long long)(t + B) * ts] - pivot;
+    const double d2 = x[(long long)(t + 2 * B) * ts] - pivot, d3 = x[(long long)(t + 3 * B) * ts] - pivot;
+    a0 += d0; a1 += d1; a2 += d2; a3 += d3;
+    q0 = fma(d0, d0, q0); q1 = fma(d1, d1, q1); q2 = fma(d2, d2, q2); q3 = fma(d3, d3, q3);
+  }
+  for (; t < S; t += B) { const double d = x[(long long)t * ts] - pivot; a0 += d; q0 = fma(d, d, q0); }
+  const double sd = drj_block_sum((a0 + a1) + (a2 + a3), sh);
+  const double sq = drj_block_sum((q0 + q1) + (q2 + q3), sh);
+  if (threadIdx.x == 0) {
+    const double md = sd / (double)S;
+    mean[(long long)c * K + k] = pivot + md;
+    var[(long long)c * K + k] = S > 1 ? fmax(sq - sd * md, 0.0) / (double)(S - 1) : 0.0;
+  }
 }
 
 // partial sums of (x_j - ctr)(x_{j+l} - ctr), l = l0 .. l0+15, over the chains CONCATENATED in chain order
-// (coda::effectiveSize is applied to the concatenated sampling draws, R/main.R:521-526)
+// (coda::effectiveSize is applied to the concatenated sampling draws, R/main.R:521-526).
+// grid = (nb, lag chunks of 16, parameters).  A CTA walks tiles of DRJ_AC_TILE consecutive elements of the
+// concatenated series: it stages x_j - ctr of the tile (xa) and of the tile shifted by l0 with a halo (xb) in
+// shared memory -- elements past the end are staged as 0, so the inner loop needs no bounds -- and every thread
+// takes PAIRS of consecutive j: one LDS.128 for (x_j, x_j+1), nine for the 18-value lag window, 32 DFMA into
+// 16 accumulators.  The first version read every operand from global memory (17 loads per 16 FMA and a 64-bit
+// division per element): 205 ms for 6.5e8 draws x 2 parameters x 89 lags, 60 % of the wall time of the ESS run.
 #define DRJ_LAGCH 16
+#define DRJ_AC_TILE 2048
+#define DRJ_AC_HALO 32
+__device__ __forceinline__ void drj_ac_stage(double* __restrict__ dst, int count, const double* __restrict__ src, long long cs,
+                                             long long ts, int S, long long N, long long j_first, double ctr) {
+  // dst[i] = x_{j_first + i} - ctr (0 past the end); one division per thread, then a carried (chain, t) walk.
+  // Eight loads are issued before the first store: one load in flight per warp left the kernel latency-bound.
+  long long j = j_first + threadIdx.x;
+  long long c = j / S;
+  int t = (int)(j - c * S);
+  const int step_c = (int)(blockDim.x / S), step_t = (int)(blockDim.x - (long long)step_c * S);
+  for (int i0 = threadIdx.x; i0 < count; i0 += 8 * blockDim.x) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v[u] = (j < N && i0 + u * (int)blockDim.x < count) ? src[c * cs + (long long)t * ts] : ctr;
+      j += blockDim.x;
+      c += step_c;
+      t += step_t;
+      if (t >= S) { t -= S; ++c; }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * (int)blockDim.x < count) dst[i0 + u * blockDim.x] = v[u] - ctr;
+  }
+}
 __global__ void __launch_bounds__(256) drj_autocov_partial(const double* __restrict__ src, long long cs, long long ts, int S,
-                                                          long long N, double ctr, int l0, int max_lag,
-                                                          double* __restrict__ partial /*[gridDim.x][DRJ_LAGCH]*/) {
+                                                          long long N, const double* __restrict__ ctrs, long long ntiles,
+                                                          double* __restrict__ partial /*[param][chunk][gridDim.x][DRJ_LAGCH]*/) {
   __shared__ double sh[8];
+  // xa = the tile, xb = the tile shifted by l0 (+ halo).  For l0 <= TILE they overlap and are staged as ONE
+  // run of TILE + l0 + HALO elements (staging is the larger half of this kernel's L2->SM traffic).
+  __shared__ __align__(16) double xs[2 * DRJ_AC_TILE + DRJ_AC_HALO];
+  const int chunk = blockIdx.y, k = blockIdx.z;
+  const int l0 = chunk * DRJ_LAGCH;
+  const double ctr = ctrs[k];
+  const double* x = src + k;
+  const bool overlap = l0 <= DRJ_AC_TILE;
+  const double* const xa = xs;
+  const double* const xb = overlap ? xs + l0 : xs + DRJ_AC_TILE;
   double acc[DRJ_LAGCH];
 #pragma unroll
   for (int q = 0; q < DRJ_LAGCH; ++q) acc[q] = 0.0;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < N; j += (long long)gridDim.x * blockDim.x) {
-    const long long c = j / S;
-    const int t = (int)(j - c * S);
-    const double xj = src[c * cs + (long long)t * ts] - ctr;
-    long long c2 = c;
-    long long t2 = (long long)t + l0;  // position of x_{j+l0}; rolls over chain boundaries
-    while (t2 >= S) { t2 -= S; ++c2; }
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long j0 = tile * DRJ_AC_TILE;
+    __syncthreads();
+    if (overlap) drj_ac_stage(xs, DRJ_AC_TILE + l0 + DRJ_AC_HALO, x, cs, ts, S, N, j0, ctr);
+    else {
+      drj_ac_stage(xs, DRJ_AC_TILE, x, cs, ts, S, N, j0, ctr);
+      drj_ac_stage(xs + DRJ_AC_TILE, DRJ_AC_TILE + DRJ_AC_HALO, x, cs, ts, S, N, j0 + l0, ctr);
+    }
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < DRJ_AC_TILE / 2; pr += blockDim.x) {
+      const double2 xj = *reinterpret_cast<const double2*>(&xa[2 * pr]);
+      double w[DRJ_LAGCH + 2];
 #pragma unroll
-    for (int q = 0; q < DRJ_LAGCH; ++q) {
-      if (l0 + q <= max_lag && j + l0 + q < N) acc[q] = fma(xj, src[c2 * cs + t2 * ts] - ctr, acc[q]);
-      if (++t2 >= S) { t2 = 0; ++c2; }
+      for (int q = 0; q < DRJ_LAGCH + 2; q += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(&xb[2 * pr + q]);
+        w[q] = v.x; w[q + 1] = v.y;
+      }
+#pragma unroll
+      for (int q = 0; q < DRJ_LAGCH; ++q) {
+        acc[q] = fma(xj.x, w[q], acc[q]);
+        acc[q] = fma(xj.y, w[q + 1], acc[q]);
+      }
     }
   }
+  double* out = partial + (((long long)k * gridDim.y + chunk) * gridDim.x + blockIdx.x) * DRJ_LAGCH;
 #pragma unroll
   for (int q = 0; q < DRJ_LAGCH; ++q) {
     const double t = drj_block_sum(acc[q], sh);
-    if (threadIdx.x == 0) partial[(long long)blockIdx.x * DRJ_LAGCH + q] = t;
+    if (threadIdx.x == 0) out[q] = t;
   }
 }
 
-__global__ void drj_reduce_partials(const double* __restrict__ partial, int nblocks, double* __restrict__ out, int l0, int max_lag) {
-  const int q = threadIdx.x;
-  if (q < DRJ_LAGCH && l0 + q <= max_lag) {
+// grid = (lag chunks, parameters): out[param][l] = sum over the CTAs of the partial kernel, fixed order
+__global__ void drj_reduce_partials(const double* __restrict__ partial, int nblocks, double* __restrict__ out, int max_lag) {
+  const int q = threadIdx.x, chunk = blockIdx.x, k = blockIdx.y;
+  const int l = chunk * DRJ_LAGCH + q;
+  if (q < DRJ_LAGCH && l <= max_lag) {
+    const double* p = partial + (((long long)k * gridDim.x + chunk) * nblocks) * DRJ_LAGCH + q;
     double t = 0.0;
-    for (int b = 0; b < nblocks; ++b) t += partial[(long long)b * DRJ_LAGCH + q];  // fixed order
-    out[l0 + q] = t;
+    for (int b = 0; b < nblocks; ++b) t += p[(long long)b * DRJ_LAGCH];
+    out[(long long)k * (max_lag + 1) + l] = t;
   }
 }
 
@@ -1130,24 +1200,35 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   const long long N = (long long)C * S;
   const int L = sm->max_lag;
   double *d_mean = nullptr, *d_var = nullptr, *d_part = nullptr, *d_ac = nullptr, *d_lm = nullptr, *d_lv = nullptr;
-  const int nb = (int)std::min<long long>(2048, (N + 255) / 256);
+  const int nchunk = L / DRJ_LAGCH + 1;
+  const long long ntiles = (N + DRJ_AC_TILE - 1) / DRJ_AC_TILE;
+  const int nb = (int)std::max<long long>(1, std::min<long long>(ntiles, 4096 / ((long long)nchunk * D) + 1));
+  double* d_ctr = nullptr;
   cudaError_t e = cudaSuccess;
-  std::vector<double> mean((size_t)C * D), var((size_t)C * D), lm(C), lv(C), ac((size_t)L + 1);
-  auto cleanup = [&]() { cudaFree(d_mean); cudaFree(d_var); cudaFree(d_part); cudaFree(d_ac); cudaFree(d_lm); cudaFree(d_lv); };
+  std::vector<double> mean((size_t)C * D), var((size_t)C * D), lm(C), lv(C), ac((size_t)D * (L + 1)), ctr(D);
+  auto cleanup = [&]() { cudaFree(d_mean); cudaFree(d_var); cudaFree(d_part); cudaFree(d_ac); cudaFree(d_lm); cudaFree(d_lv); cudaFree(d_ctr); };
 #define SUM_TRY(call) do { e = (call); if (e != cudaSuccess) { cleanup(); CUDA_TRY(e); } } while (0)
   SUM_TRY(cudaMalloc(&d_mean, sizeof(double) * (size_t)C * D));
   SUM_TRY(cudaMalloc(&d_var, sizeof(double) * (size_t)C * D));
   SUM_TRY(cudaMalloc(&d_lm, sizeof(double) * (size_t)C));
   SUM_TRY(cudaMalloc(&d_lv, sizeof(double) * (size_t)C));
-  SUM_TRY(cudaMalloc(&d_part, sizeof(double) * (size_t)nb * DRJ_LAGCH));
-  SUM_TRY(cudaMalloc(&d_ac, sizeof(double) * ((size_t)L + 1)));
-  drj_chain_moments<<<dim3(C, D), 256, 0, s->stream>>>(th, th_cs, th_ts, 1, S, D, d_mean, d_var);
-  drj_chain_moments<<<dim3(C, 1), 256, 0, s->stream>>>(ll, ll_cs, 1, 0, S, 1, d_lm, d_lv);
-  s->aux_launches += 2;
-  SUM_TRY(cudaMemcpyAsync(mean.data(), d_mean, sizeof(double) * mean.size(), cudaMemcpyDeviceToHost, s->stream));
-  SUM_TRY(cudaMemcpyAsync(var.data(), d_var, sizeof(double) * var.size(), cudaMemcpyDeviceToHost, s->stream));
-  SUM_TRY(cudaMemcpyAsync(lm.data(), d_lm, sizeof(double) * lm.size(), cudaMemcpyDeviceToHost, s->stream));
-  SUM_TRY(cudaMemcpyAsync(lv.data(), d_lv, sizeof(double) * lv.size(), cudaMemcpyDeviceToHost, s->stream));
+  SUM_TRY(cudaMalloc(&d_part, sizeof(double) * (size_t)D * nchunk * nb * DRJ_LAGCH));
+  SUM_TRY(cudaMalloc(&d_ac, sizeof(double) * (size_t)D * (L + 1)));
+  SUM_TRY(cudaMalloc(&d_ctr, sizeof(double) * (size_t)D));
+  // only what the caller asked for (each part is a pass over the stored draws)
+  const bool want_theta_moments = sm->chain_mean || sm->chain_var || (sm->autocov_sum && !sm->center);
+  if (want_theta_moments) {
+    drj_chain_moments<<<dim3(C, D), 256, 0, s->stream>>>(th, th_cs, th_ts, 1, S, D, d_mean, d_var);
+    s->aux_launches++;
+    SUM_TRY(cudaMemcpyAsync(mean.data(), d_mean, sizeof(double) * mean.size(), cudaMemcpyDeviceToHost, s->stream));
+    SUM_TRY(cudaMemcpyAsync(var.data(), d_var, sizeof(double) * var.size(), cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (sm->deviance_mean_var) {
+    drj_chain_moments<<<dim3(C, 1), 256, 0, s->stream>>>(ll, ll_cs, 1, 0, S, 1, d_lm, d_lv);
+    s->aux_launches++;
+    SUM_TRY(cudaMemcpyAsync(lm.data(), d_lm, sizeof(double) * lm.size(), cudaMemcpyDeviceToHost, s->stream));
+    SUM_TRY(cudaMemcpyAsync(lv.data(), d_lv, sizeof(double) * lv.size(), cudaMemcpyDeviceToHost, s->stream));
+  }
   SUM_TRY(cudaStreamSynchronize(s->stream));
   if (sm->chain_mean) memcpy(sm->chain_mean, mean.data(), sizeof(double) * mean.size());
   if (sm->chain_var) memcpy(sm->chain_var, var.data(), sizeof(double) * var.size());
@@ -1163,18 +1244,21 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   }
   if (sm->autocov_sum) {
     for (int k = 0; k < D; ++k) {
-      double ctr;
-      if (sm->center) ctr = sm->center[k];
-      else { ctr = 0.0; for (int c = 0; c < C; ++c) ctr += mean[(size_t)c * D + k]; ctr /= C; }
-      for (int l0 = 0; l0 <= L; l0 += DRJ_LAGCH) {
-        drj_autocov_partial<<<nb, 256, 0, s->stream>>>(th + k, th_cs, th_ts, S, N, ctr, l0, L, d_part);
-        drj_reduce_partials<<<1, 32, 0, s->stream>>>(d_part, nb, d_ac, l0, L);
-        s->aux_launches += 2;
-      }
-      SUM_TRY(cudaMemcpyAsync(ac.data(), d_ac, sizeof(double) * ac.size(), cudaMemcpyDeviceToHost, s->stream));
-      SUM_TRY(cudaStreamSynchronize(s->stream));
-      memcpy(sm->autocov_sum + (size_t)k * (L + 1), ac.data(), sizeof(double) * ac.size());
+      if (sm->center) ctr[k] = sm->center[k];
+      else { double t = 0.0; for (int c = 0; c < C; ++c) t += mean[(size_t)c * D + k]; ctr[k] = t / C; }
     }
+    SUM_TRY(cudaMemcpyAsync(d_ctr, ctr.data(), sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, s->stream));
+    for (int k0 = 0; k0 < D; k0 += 65535) {  // grid.z limit
+      const int nk = std::min(D - k0, 65535);
+      drj_autocov_partial<<<dim3(nb, nchunk, nk), 256, 0, s->stream>>>(th + k0, th_cs, th_ts, S, N, d_ctr + k0, ntiles,
+                                                                       d_part + (size_t)k0 * nchunk * nb * DRJ_LAGCH);
+      drj_reduce_partials<<<dim3(nchunk, nk), 32, 0, s->stream>>>(d_part + (size_t)k0 * nchunk * nb * DRJ_LAGCH, nb,
+                                                                  d_ac + (size_t)k0 * (L + 1), L);
+      s->aux_launches += 2;
+    }
+    SUM_TRY(cudaMemcpyAsync(ac.data(), d_ac, sizeof(double) * ac.size(), cudaMemcpyDeviceToHost, s->stream));
+    SUM_TRY(cudaStreamSynchronize(s->stream));
+    memcpy(sm->autocov_sum, ac.data(), sizeof(double) * ac.size());
   }
   if ((sm->head || sm->tail) && L > 0) {
     double *d_head = nullptr, *d_tail = nullptr;

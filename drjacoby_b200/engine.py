@@ -235,9 +235,11 @@ class Session:
         L.lib().drj_session_timing(self._h, C.byref(a), C.byref(b))
         return float(a.value), float(b.value)
 
-    def summary(self, max_lag: int | None = None, center=None) -> dict:
+    def summary(self, max_lag: int | None = None, center=None, moments: bool = True, autocov: bool = True) -> dict:
         """On-device summaries of the cold-rung sampling draws (drj_session_summary): per-chain means and
-        variances, autocovariance sums of the concatenated chains, deviance mean / variance."""
+        variances, autocovariance sums of the concatenated chains, deviance mean / variance.  Each part is a
+        pass over the stored draws: `moments=False` / `autocov=False` skip the ones not needed (skipped parts
+        come back as zeros)."""
         sp = self.spec
         n_tot = sp.chains * sp.samples
         if max_lag is None:
@@ -251,9 +253,14 @@ class Session:
         if center is not None:
             ctr = np.ascontiguousarray(center, dtype=np.float64)
             sm.center = L.dptr(ctr)
-        sm.chain_mean, sm.chain_var = L.dptr(out["chain_mean"]), L.dptr(out["chain_var"])
-        sm.autocov_sum, sm.deviance_mean_var = L.dptr(out["autocov_sum"]), L.dptr(out["deviance_mean_var"])
-        sm.head, sm.tail = L.dptr(out["head"]), L.dptr(out["tail"])
+        if moments:
+            sm.chain_mean, sm.chain_var = L.dptr(out["chain_mean"]), L.dptr(out["chain_var"])
+            sm.deviance_mean_var = L.dptr(out["deviance_mean_var"])
+        if autocov:
+            if center is None and not moments:
+                raise ValueError("autocov without moments needs a center")
+            sm.autocov_sum = L.dptr(out["autocov_sum"])
+            sm.head, sm.tail = L.dptr(out["head"]), L.dptr(out["tail"])
         err = L.DrjError()
         rc = L.lib().drj_session_summary(self._h, C.byref(sm), C.byref(err))
         L.raise_for(rc, err, sp.d)

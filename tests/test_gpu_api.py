@@ -410,3 +410,37 @@ def test_multi_block_datum_form_model(n):
         np.testing.assert_allclose(a.raw[k], b.raw[k], rtol=1e-10, atol=1e-12)
     if n > 0:
         assert abs(a.raw["theta_sampling"][:, 0, :, 0].mean() - data["x"].mean()) < 0.5
+
+
+@pytest.mark.parametrize("chains,samples,max_lag,hot", [(300, 37, 2100, False), (3, 5000, 40, True), (1, 2049, 17, False)])
+def test_on_device_autocovariance_edge_geometries(chains, samples, max_lag, hot):
+    """drj_session_summary against numpy on the downloaded draws: chains shorter than a CTA (several chain
+    boundaries inside one staging step), lags beyond one tile (the two-region staging path), hot draws stored
+    (cold rung strided), a series ending one element into a tile."""
+    from drjacoby_b200 import engine
+    x = np.random.default_rng(5).normal(3, 2, 30)
+    rungs = 3 if hot else 1
+    init = np.tile(np.array([3.0, 2.0]), (chains, 1))
+    spec = engine.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=init, burnin=20, samples=samples,
+                          beta_raised=np.linspace(0, 1, rungs) if rungs > 1 else [1.0], save_hot_draws=hot, rng_mode="philox",
+                          seed=11, data=[x])
+    s = engine.Session(engine.Model(builtin="example"), spec)
+    s.advance(spec.T)
+    full = s.download()
+    th = full["theta_sampling"][:, -1]                      # cold rung [chains, samples, d]
+    series = th.reshape(chains * samples, 2)
+    center = series.mean(axis=0) + np.array([0.01, -0.02])  # any centre
+    sm = s.summary(max_lag=max_lag, center=center)
+    only_ac = s.summary(max_lag=max_lag, center=center, moments=False)
+    s.close()
+    n = series.shape[0]
+    for k in range(2):
+        xc = series[:, k] - center[k]
+        want = np.array([xc[: n - l] @ xc[l:] for l in range(max_lag + 1)])
+        np.testing.assert_allclose(sm["autocov_sum"][k], want, rtol=1e-9, atol=1e-9 * abs(want[0]))
+        assert np.array_equal(sm["autocov_sum"][k], only_ac["autocov_sum"][k])
+        np.testing.assert_array_equal(sm["head"][k], series[:max_lag, k])
+        np.testing.assert_array_equal(sm["tail"][k], series[n - max_lag:, k])
+    np.testing.assert_allclose(sm["chain_mean"], th.mean(axis=1), rtol=1e-12)
+    np.testing.assert_allclose(sm["chain_var"], th.var(axis=1, ddof=1), rtol=1e-9)
+    assert not only_ac["chain_mean"].any()
