@@ -27,7 +27,7 @@ import numpy as np
 import pandas as pd
 
 from . import diagnostics as dg
-from . import engine
+from . import _lib, engine
 from ._lib import DrjacobyError
 from .rcompat import RStream
 
@@ -332,12 +332,19 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
         # the reference runs chains one after another on one stream: chain c owns uniforms [c*T*U, (c+1)*T*U)
         allu = rstream.runif(chains * T * U)
         replay = allu[lo * T * U: hi * T * U]
+    flags = 0
+    if cluster is not None:
+        # the kernel family (one thread per particle / one cluster per chain) is chosen from the shard's size; the two
+        # associate the likelihood sum differently (equal within 1e-10, not bitwise).  Decide from the WHOLE run's size so
+        # that every shard -- and the same run on one GPU -- uses the same family and stays bit-identical.
+        longest = max([len(v) for v in data_items], default=0)
+        flags = _lib.FLAG_TEAM_KERNEL if (longest > 4096 and chains * rungs <= 4096) else _lib.FLAG_NO_TEAM_KERNEL
     spec = engine.RunSpec(theta_min=tmin, theta_max=tmax, theta_init=init_mat.T[lo:hi], burnin=burnin, samples=samples,
                           beta_raised=beta_raised, blocks=[list(b) for b in df_params["block"]], coupling_on=bool(coupling_on),
                           save_hot_draws=bool(save_hot_draws), store_pt=bool(store_pt), target_acceptance=float(target_acceptance),
                           rng_mode="replay" if rng == "r" else "philox", seed=0 if seed is None or rng == "r" else int(seed),
                           chain_offset=lo, replay=replay, device=device, data=data_items, misc=misc_items,
-                          data_names=data_names, misc_names=misc_names, param_names=list(df_params["name"]))
+                          data_names=data_names, misc_names=misc_names, param_names=list(df_params["name"]), flags=flags)
 
     # ---------- run (one native call for all chains of this rank; R/main.R:392-402 loops chains instead)
     phase_names = ("burn-in", "sampling phase")

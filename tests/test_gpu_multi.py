@@ -19,4 +19,4 @@ def test_two_gpu_run_equals_one_gpu_run():
                           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "multi_gpu_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "OK full" in out.stdout and "OK summary" in out.stdout
+    assert "OK full" in out.stdout and "OK summary" in out.stdout and "OK few chains" in out.stdout

@@ -29,5 +29,15 @@ if rank == 0:
         assert rel < 1e-9, rel   # including the lag products that straddle the shard boundary
     assert abs(summ.diagnostics["DIC_Gelman"] - one.diagnostics["DIC_Gelman"]) < 1e-9 * abs(one.diagnostics["DIC_Gelman"])
     print("OK summary: Rhat equal, ESS rel diff", rel, ", DIC equal")
+# few chains over a long data vector: every shard uses the cluster-per-chain kernels, as the one-GPU run does
+xl = np.random.default_rng(2).normal(3, 2, 30001)
+kw = dict(data={"x": xl}, df_params=df, loglike="loglike", logprior="logprior", burnin=30, samples=60, rungs=3, chains=5, seed=9, silent=True)
+few = drj.run_mcmc(cluster="torch", **kw)
+if rank == 0:
+    one = drj.run_mcmc(device=0, **kw)
+    for k, v in one.raw.items():
+        if k != "t_diff":
+            assert np.array_equal(few.raw[k], v), k
+    print("OK few chains: 5 chains x 3 rungs over n = 30001, sharded == single GPU, bit for bit")
 dist.barrier()
 dist.destroy_process_group()
