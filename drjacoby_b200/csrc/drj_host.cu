@@ -464,10 +464,10 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_stream(const __grid_constant__ DrjKernelArgs a) {\n"
        "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true, false>(a);\n"
        "}\n"
-       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_init_team(const __grid_constant__ DrjKernelArgs a) {\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_user_init_team(const __grid_constant__ DrjKernelArgs a) {\n"
        "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_init_body<DRJ_USER_MODEL, true>(a);\n"
        "}\n"
-       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_sweep_team(const __grid_constant__ DrjKernelArgs a) {\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_user_sweep_team(const __grid_constant__ DrjKernelArgs a) {\n"
        "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, false, true>(a);\n"
        "}\n"
        "extern \"C\" __global__ void drj_user_traits(int* out) { out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0; }\n";
@@ -477,7 +477,7 @@ static std::string make_jit_source(const drj_model_desc* desc) {
 static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
   const double t0 = wall_now();
   const std::string src = make_jit_source(desc);
-  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v2";
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v3";
   char hex[32];
   snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)fnv1a(key_text));
   const std::string path = cache_dir() + "/" + hex + ".cubin";
@@ -1025,8 +1025,8 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
       }
       if (const char* e = getenv("DRJ_TEAM_STAGES")) team_stages = std::max(2, std::min(3, atoi(e)));
       s->team_ctas = K;
-      s->cpc = DRJ_NT / R;  // slots per rung in a CTA
-      s->nthreads = DRJ_NT;
+      s->cpc = DRJ_TEAM_NT / R;  // slots per rung in a CTA
+      s->nthreads = DRJ_TEAM_NT;
     }
   }
 

@@ -196,6 +196,9 @@ __device__ __forceinline__ double* drj_tile_buf() {
 #define DRJ_TEAM_MAXSTAGES 12  // TEAM kernels: at most this many tiles in flight per CTA
 #define DRJ_TEAM_VRANKS 16     // TEAM kernels: canonical number of partial sums a data item is split into
 #define DRJ_TEAM_MAXR 32       // TEAM kernels: at most this many rungs
+#ifndef DRJ_TEAM_NT
+#define DRJ_TEAM_NT 256        // TEAM kernels: threads per CTA (512, at a 128-register cap, measured 5-10 % slower on every shape)
+#endif
 template <class M>
 __device__ __forceinline__ unsigned long long* drj_tile_bars() {
   __shared__ __align__(8) unsigned long long s_full[DRJ_TEAM_MAXSTAGES];
@@ -205,7 +208,7 @@ __device__ __forceinline__ unsigned long long* drj_tile_bars() {
 // [parity][virtual rank][rung] every CTA of the cluster receives from its peers
 template <class M>
 __device__ __forceinline__ double* drj_team_red() {
-  __shared__ double s_red[DRJ_NT];
+  __shared__ double s_red[DRJ_TEAM_NT];
   return s_red;
 }
 template <class M>
@@ -713,7 +716,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
     s_tmin[i] = a.theta_min[i]; s_tmax[i] = a.theta_max[i];
     s_trans[i] = a.trans_type[i]; s_free[i] = a.free_slot[i];
   }
-  s_mc[tid] = 0;
+  if (tid < DRJ_NT) s_mc[tid] = 0;  // (TEAM CTAs have more threads than DRJ_NT; only slot 0, tid < R, uses these arrays)
 
   DrjTiles<M> T;
   T.template init<TEAM>(a);
@@ -843,8 +846,8 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
     // ================= Metropolis coupling (main.cpp:282-344) =================
     if (do_couple) {
-      s_x[tid] = s.ll;
-      if (r < R - 1) {
+      if (!TEAM || tid < R) s_x[tid] = s.ll;
+      if (r < R - 1 && (!TEAM || tid < R)) {
         double u;
         if (a.rng_mode) u = rp[3LL * a.d_free * R + r];
         else {
@@ -908,7 +911,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
               else if (v < 4 * D + B) val = s.llb[v - 4 * D];
               else if (v == 4 * D + B) val = s.ll;
               else val = s.lp;
-              s_x[e * DRJ_NT + tid] = val;
+              if (!TEAM || tid < R) s_x[e * DRJ_NT + tid] = val;
             }
           }
           drj_sync(wl);
@@ -959,11 +962,11 @@ __global__ void __launch_bounds__(DRJ_NT, (STREAM ? 2 : DRJ_MINB)) drj_sweep_ker
 }
 // cluster-per-chain variants (launched with a cluster dimension of a.team_ctas; datum-form models only)
 template <class M>
-__global__ void __launch_bounds__(DRJ_NT, 1) drj_init_kernel_team(const __grid_constant__ DrjKernelArgs a) {
+__global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_init_kernel_team(const __grid_constant__ DrjKernelArgs a) {
   drj_init_body<M, true>(a);
 }
 template <class M>
-__global__ void __launch_bounds__(DRJ_NT, 1) drj_sweep_kernel_team(const __grid_constant__ DrjKernelArgs a) {
+__global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_sweep_kernel_team(const __grid_constant__ DrjKernelArgs a) {
   drj_sweep_body<M, false, true>(a);
 }
 // addresses of the variants that only exist for datum-form models
