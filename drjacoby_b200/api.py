@@ -219,7 +219,7 @@ def _flatten_list(d: dict, what: str):
 def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3, samples=1e4, rungs=1, chains=5,
              beta_manual=None, alpha=1.0, target_acceptance=0.44, cluster=None, coupling_on=True, pb_markdown=False,
              save_data=True, save_hot_draws=False, silent=False, *, source: CudaSource | None = None, seed=None,
-             rng="philox", store_pt=True, device=None, as_frames=True, progress=None, output="full") -> DrjacobyOutput:
+             rng="philox", store_pt=True, device=None, as_frames=True, progress=None, output="full", thin=None) -> DrjacobyOutput:
     """run_mcmc() of the reference (R/main.R:208-225) on the GPU.
 
     Extra keyword-only arguments: `source` (a CudaSource; default: the last source_cuda()/use_builtin()),
@@ -229,6 +229,10 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
     (build the data frames; False keeps only `.raw` for very large runs), `output` ("full": every draw comes
     back, as in the reference; "summary": the draws stay in GPU memory and Rhat / ESS / DIC are computed from
     on-device reductions -- for runs whose draws are too large to move).
+    `thin` (with output="summary"): additionally bring back every thin-th stored draw of the cold rung, gathered on
+    the device, as the usual `output` data frame with the original iteration numbers -- diagnostics stay exact (all
+    draws, on the device), plots and quantiles work on the thinned frame (sample_chains() of the reference subsamples
+    after the fact, R/samples.R; here the full set never has to leave the GPU).
     `cluster`: None = this process's GPU; "torch" = shard chains over the ranks of an initialised
     torch.distributed group (one process per GPU), results gathered on rank 0.
     """
@@ -360,16 +364,25 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
 
     if output not in ("full", "summary"):
         raise ValueError('output must be "full" or "summary"')
+    if thin is not None:
+        if output != "summary":
+            raise ValueError('thin= needs output="summary" (with output="full" every draw comes back; subsample with sample_chains())')
+        if int(thin) != thin or thin < 1:
+            raise ValueError("thin must be a positive integer")
+        thin = int(thin)
     if output == "summary":
         raw, diagnostics = _run_summary(model, spec, _progress if not (silent and progress is None) else None, names=list(df_params["name"]),
-                                        skip_param=skip_param, chains=chains, rank=rank, world=world, beta_raised=beta_raised)
+                                        skip_param=skip_param, chains=chains, rank=rank, world=world, beta_raised=beta_raised, thin=thin)
         if rank != 0:
             return None
+        frame = None
+        if thin is not None and as_frames:
+            frame = _thinned_frame(raw, list(df_params["name"]), burnin, samples, thin, chains)
         parameters = dict(data=data if save_data else None, df_params=df_params, loglike=loglike, logprior=logprior,
                           burnin=burnin, samples=samples, rungs=rungs, chains=chains, coupling_on=bool(coupling_on), alpha=alpha,
                           beta_manual=beta_manual)
         diagnostics["wall_seconds"] = time.perf_counter() - t_start
-        return DrjacobyOutput(None, None, diagnostics, parameters, raw)
+        return DrjacobyOutput(frame, None, diagnostics, parameters, raw)
     raw = _run_shard(model, spec, None if (silent and progress is None) else _progress)
     if cluster is not None:
         raw = gather_shards(raw, chains, rank, world)
@@ -396,7 +409,25 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
     return res
 
 
-def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, world, beta_raised):
+def _thinned_frame(raw, names, burnin, samples, thin, chains):
+    """The `output` data frame (cold rung) from draws thinned on the device: stored iterations 0, thin, 2 thin, ... of
+    each phase, numbered as the reference numbers them (1..burnin, burnin+1..burnin+samples; R/main.R:420-476)."""
+    th_b, th_s = raw["theta_burnin"][:, -1], raw["theta_sampling"][:, -1]  # [chains, kept, d]
+    it_b = 1 + thin * np.arange(th_b.shape[1])
+    it_s = burnin + 1 + thin * np.arange(th_s.shape[1])
+    n_it = it_b.size + it_s.size
+    out = pd.DataFrame({"chain": np.repeat(np.arange(1, chains + 1), n_it),
+                        "phase": np.tile(np.concatenate([np.repeat("burnin", it_b.size), np.repeat("sampling", it_s.size)]), chains),
+                        "iteration": np.tile(np.concatenate([it_b, it_s]), chains)})
+    theta = np.concatenate([th_b, th_s], axis=1).reshape(chains * n_it, len(names))
+    for k, nm in enumerate(names):
+        out[nm] = theta[:, k]
+    out["logprior"] = np.concatenate([raw["logprior_burnin"][:, -1], raw["logprior_sampling"][:, -1]], axis=1).ravel()
+    out["loglikelihood"] = np.concatenate([raw["loglike_burnin"][:, -1], raw["loglike_sampling"][:, -1]], axis=1).ravel()
+    return out
+
+
+def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, world, beta_raised, thin=None):
     """output="summary": run the shard in a session, reduce the draws on the device, bring back only the
     summaries and counters; across ranks the per-chain moments are gathered and the autocovariance sums
     (about the global mean) added, plus the lag products that straddle two ranks' shards (from each shard's
@@ -446,7 +477,7 @@ def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, worl
                     for lag in range(1, max_lag + 1):
                         # x_j in the last `lag` draws of shard k pairs with x_{j+lag} among the first `lag` of shard k+1
                         ac[:, lag] += (tl[:, max_lag - lag:] * hd[:, :lag]).sum(axis=1)
-        raw = sess.download(draws=False)
+        raw = sess.download(draws=False) if thin is None else sess.download(draws=True, thin=thin)
         if world > 1:
             raw = gather_shards(raw, chains, rank, world)
     finally:

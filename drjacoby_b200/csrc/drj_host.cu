@@ -227,6 +227,19 @@ __global__ void drj_reduce_partials(const double* __restrict__ partial, int nblo
   }
 }
 
+// every thin-th row of every series: dst[(q * n_keep + j) * w + c] = src[(q * n + j * thin) * w + c]
+__global__ void __launch_bounds__(256) drj_thin_rows(const double* __restrict__ src, double* __restrict__ dst, long long n_series,
+                                                    int n, int n_keep, int w, int thin) {
+  const long long total = n_series * n_keep * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / w;
+    const int c = (int)(i - row * w);
+    const long long q = row / n_keep;
+    const int j = (int)(row - q * n_keep);
+    dst[i] = src[(q * n + (long long)j * thin) * w + c];
+  }
+}
+
 // the first / last L elements of the concatenated series of every parameter: out[k][i]
 __global__ void drj_series_ends(const double* __restrict__ src, long long cs, long long ts, int S, long long N, int D, int L,
                                 double* __restrict__ head, double* __restrict__ tail) {
@@ -1297,20 +1310,48 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   return DRJ_OK;
 }
 
+// draws to the host; thin > 1 keeps the stored iterations 0, thin, 2 thin, ... of every series (gathered on the
+// device into a compact buffer first), so the caller's arrays hold ceil(n / thin) rows per series
+static int copy_series(drj_session* s, double* dst, const double* src, long long n_series, int n, int w, int thin, drj_error* err) {
+  if (!dst) return DRJ_OK;
+  if (thin <= 1) {
+    CUDA_TRY(cudaMemcpy(dst, src, sizeof(double) * (size_t)n_series * n * w, cudaMemcpyDeviceToHost));
+    return DRJ_OK;
+  }
+  const int n_keep = (n + thin - 1) / thin;
+  const size_t bytes = sizeof(double) * (size_t)n_series * n_keep * w;
+  double* tmp = nullptr;
+  CUDA_TRY(cudaMalloc(&tmp, std::max<size_t>(bytes, 8)));
+  const long long total = n_series * n_keep * w;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148 * 16));
+  drj_thin_rows<<<grid, 256, 0, s->stream>>>(src, tmp, n_series, n, n_keep, w, thin);
+  s->aux_launches++;
+  cudaError_t e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(tmp);
+  CUDA_TRY(e);
+  return DRJ_OK;
+}
+
 extern "C" int drj_session_download(drj_session* s, drj_output* out, drj_error* err) {
+  return drj_session_download_thinned(s, 1, out, err);
+}
+
+extern "C" int drj_session_download_thinned(drj_session* s, int thin, drj_output* out, drj_error* err) {
   if (!s || !out) return set_err(err, DRJ_ERR_ARG, "NULL session or output");
+  if (thin < 1) return set_err(err, DRJ_ERR_ARG, "thin must be >= 1");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   const drj_config& c = s->cfg;
-  const size_t nb = c.burnin, ns = c.samples;
+  int rc;
+  if ((rc = copy_series(s, out->loglike_burnin, s->fin_ll_b, s->Ppt, c.burnin, 1, thin, err))) return rc;
+  if ((rc = copy_series(s, out->logprior_burnin, s->fin_lp_b, s->Ppt, c.burnin, 1, thin, err))) return rc;
+  if ((rc = copy_series(s, out->theta_burnin, s->fin_th_b, s->Pth, c.burnin, s->D, thin, err))) return rc;
+  if ((rc = copy_series(s, out->loglike_sampling, s->fin_ll_s, s->Ppt, c.samples, 1, thin, err))) return rc;
+  if ((rc = copy_series(s, out->logprior_sampling, s->fin_lp_s, s->Ppt, c.samples, 1, thin, err))) return rc;
+  if ((rc = copy_series(s, out->theta_sampling, s->fin_th_s, s->Pth, c.samples, s->D, thin, err))) return rc;
 #define D2H(dst, src, n) \
   if (dst) CUDA_TRY(cudaMemcpy(dst, src, (n), cudaMemcpyDeviceToHost))
-  D2H(out->loglike_burnin, s->fin_ll_b, sizeof(double) * s->Ppt * nb);
-  D2H(out->logprior_burnin, s->fin_lp_b, sizeof(double) * s->Ppt * nb);
-  D2H(out->theta_burnin, s->fin_th_b, sizeof(double) * s->Pth * nb * s->D);
-  D2H(out->loglike_sampling, s->fin_ll_s, sizeof(double) * s->Ppt * ns);
-  D2H(out->logprior_sampling, s->fin_lp_s, sizeof(double) * s->Ppt * ns);
-  D2H(out->theta_sampling, s->fin_th_s, sizeof(double) * s->Pth * ns * s->D);
   if (s->R > 1) {
     D2H(out->mc_accept_burnin, s->mc_b, sizeof(int) * (size_t)s->C * (s->R - 1));
     D2H(out->mc_accept_sampling, s->mc_s, sizeof(int) * (size_t)s->C * (s->R - 1));

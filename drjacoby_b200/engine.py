@@ -152,15 +152,20 @@ class RunSpec:
         c.iters_per_launch, c.chains_per_cta, c.flags = self.iters_per_launch, self.chains_per_cta, self.flags
         return c
 
-    def alloc_outputs(self) -> dict:
+    def alloc_outputs(self, thin: int = 1, draws: bool = True) -> dict:
         C_, R, d = self.chains, self.rungs, self.d
         ptR = R if self.store_pt else 1
         thR = R if self.save_hot_draws else 1
+        nb, ns = -(-self.burnin // thin), -(-self.samples // thin)
+        out = {}
+        if draws:
+            out = dict(
+                loglike_burnin=np.zeros((C_, ptR, nb)), logprior_burnin=np.zeros((C_, ptR, nb)),
+                theta_burnin=np.zeros((C_, thR, nb, d)),
+                loglike_sampling=np.zeros((C_, ptR, ns)), logprior_sampling=np.zeros((C_, ptR, ns)),
+                theta_sampling=np.zeros((C_, thR, ns, d)))
         return dict(
-            loglike_burnin=np.zeros((C_, ptR, self.burnin)), logprior_burnin=np.zeros((C_, ptR, self.burnin)),
-            theta_burnin=np.zeros((C_, thR, self.burnin, d)),
-            loglike_sampling=np.zeros((C_, ptR, self.samples)), logprior_sampling=np.zeros((C_, ptR, self.samples)),
-            theta_sampling=np.zeros((C_, thR, self.samples, d)),
+            out,
             mc_accept_burnin=np.zeros((C_, max(R - 1, 0)), np.int32),
             mc_accept_sampling=np.zeros((C_, max(R - 1, 0)), np.int32),
             accept_burnin=np.zeros((C_, R), np.int32), accept_sampling=np.zeros((C_, R), np.int32),
@@ -267,16 +272,17 @@ class Session:
         out["max_lag"] = int(max_lag)
         return out
 
-    def download(self, draws: bool = True) -> dict:
+    def download(self, draws: bool = True, thin: int = 1) -> dict:
         """All outputs, or (draws=False) only the counters / run times / bandwidths: the stored draws stay
-        on the device (summary mode for runs whose draws are too large to move)."""
-        out = self.spec.alloc_outputs()
-        if not draws:
-            for k in _DRAW_KEYS:
-                del out[k]
+        on the device (summary mode for runs whose draws are too large to move).  thin > 1: only the stored
+        iterations 0, thin, 2 thin, ... of every series come back (gathered on the device)."""
+        thin = int(thin)
+        if thin < 1:
+            raise ValueError("thin must be >= 1")
+        out = self.spec.alloc_outputs(thin if draws else 1, draws)
         cout = _c_output(out)
         err = L.DrjError()
-        rc = L.lib().drj_session_download(self._h, C.byref(cout), C.byref(err))
+        rc = L.lib().drj_session_download_thinned(self._h, thin, C.byref(cout), C.byref(err))
         L.raise_for(rc, err, self.spec.d)
         return out
 

@@ -192,6 +192,11 @@ int drj_session_create(const drj_config* cfg, const drj_model* model, const drj_
 int drj_session_advance(drj_session* s, int n_iter, float* kernel_ms, drj_error* err);
 int drj_session_iterations_done(const drj_session* s); /* rows stored so far, incl. the initial row */
 int drj_session_download(drj_session* s, drj_output* out, drj_error* err); /* NULL members of *out are skipped */
+/* The same with every `thin`-th stored iteration only (0, thin, 2 thin, ...): the draw arrays of *out hold
+ * ceil(burnin / thin) resp. ceil(samples / thin) rows per series, the counters are complete.  For runs whose
+ * draws are too large to move whole ("summary / thinned modes"); the reference has no thinning
+ * inside run_mcmc, its sample_chains() subsamples afterwards (R/samples.R). */
+int drj_session_download_thinned(drj_session* s, int thin, drj_output* out, drj_error* err);
 int drj_session_summary(drj_session* s, drj_summary* summary, drj_error* err);
 int drj_session_launches(const drj_session* s, int64_t* sweep_launches, int64_t* aux_launches);
 /* cumulative CUDA-event time on the session's stream: sweep kernels only / sweep kernels + output transposes */

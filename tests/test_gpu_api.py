@@ -5,6 +5,7 @@ import json
 import os
 
 import numpy as np
+import pandas as pd
 import pytest
 from scipy import stats
 
@@ -444,3 +445,41 @@ def test_on_device_autocovariance_edge_geometries(chains, samples, max_lag, hot)
     np.testing.assert_allclose(sm["chain_mean"], th.mean(axis=1), rtol=1e-12)
     np.testing.assert_allclose(sm["chain_var"], th.var(axis=1, ddof=1), rtol=1e-9)
     assert not only_ac["chain_mean"].any()
+
+
+@pytest.mark.parametrize("thin", [1, 7, 100, 5000])
+def test_thinned_download_equals_slicing_the_full_download(thin):
+    """drj_session_download_thinned: stored iterations 0, thin, 2 thin, ... of every series, gathered on the device."""
+    from drjacoby_b200 import engine
+    x = np.random.default_rng(5).normal(3, 2, 30)
+    spec = engine.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=np.tile([3.0, 2.0], (6, 1)), burnin=45,
+                          samples=301, beta_raised=np.linspace(0, 1, 3), save_hot_draws=True, rng_mode="philox", seed=4, data=[x])
+    s = engine.Session(engine.Model(builtin="example"), spec)
+    s.advance(spec.T)
+    full, thinned = s.download(), s.download(thin=thin)
+    s.close()
+    for k in ("loglike_burnin", "logprior_burnin", "loglike_sampling", "logprior_sampling"):
+        assert np.array_equal(thinned[k], full[k][:, :, ::thin]), k
+    for k in ("theta_burnin", "theta_sampling"):
+        assert np.array_equal(thinned[k], full[k][:, :, ::thin, :]), k
+    for k in ("accept_burnin", "accept_sampling", "mc_accept_burnin", "mc_accept_sampling", "bw_final"):
+        assert np.array_equal(thinned[k], full[k]), k
+
+
+def test_summary_mode_with_thinned_draws():
+    """run_mcmc(output="summary", thin=k): exact diagnostics from all draws on the device + every k-th draw as the
+    usual output frame with the reference's iteration numbering."""
+    x = np.random.default_rng(3).normal(3, 2, 40)
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+    drj.source_cuda(NORMAL_SRC)
+    kw = dict(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=100, samples=1000, rungs=3, chains=4,
+              seed=8, silent=True)
+    full = drj.run_mcmc(**kw)
+    thin = drj.run_mcmc(output="summary", thin=10, **kw)
+    assert thin.pt is None and thin.diagnostics["rhat"]["mu"] == full.diagnostics["rhat"]["mu"]
+    assert abs(thin.diagnostics["ess"]["sigma"] - full.diagnostics["ess"]["sigma"]) <= 1e-8 * full.diagnostics["ess"]["sigma"]
+    keep = full.output[((full.output["iteration"] - 1) % 10 == 0)].reset_index(drop=True)
+    assert len(thin.output) == 4 * (10 + 100) and list(thin.output.columns) == list(full.output.columns)
+    pd.testing.assert_frame_equal(thin.output, keep)
+    with pytest.raises(ValueError):
+        drj.run_mcmc(thin=10, **kw)
