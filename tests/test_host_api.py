@@ -200,3 +200,34 @@ def test_shard_ranges():
             r = [api.shard_range(chains, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == chains and all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_thinned_frame_numbering_and_shapes():
+    """Host side of run_mcmc(output="summary", thin=k): output-buffer shapes for a thinned download and the
+    iteration numbers of the frame built from it (the reference numbers 1..burnin, burnin+1..burnin+samples)."""
+    from drjacoby_b200 import engine
+    spec = engine.RunSpec(theta_min=[-1.0, 0.0], theta_max=[1.0, 5.0], theta_init=np.zeros((3, 2)) + 0.5, burnin=10, samples=25,
+                          beta_raised=[0.0, 1.0], save_hot_draws=True)
+    o = spec.alloc_outputs(thin=4)
+    assert o["theta_burnin"].shape == (3, 2, 3, 2) and o["theta_sampling"].shape == (3, 2, 7, 2)
+    assert o["loglike_sampling"].shape == (3, 2, 7) and o["accept_sampling"].shape == (3, 2)
+    assert "theta_sampling" not in spec.alloc_outputs(draws=False)
+    raw = {k: np.arange(v.size, dtype=float).reshape(v.shape) for k, v in o.items()}
+    f = api._thinned_frame(raw, ["a", "b"], 10, 25, 4, 3)
+    one = f[f["chain"] == 2]
+    assert one["iteration"].tolist() == [1, 5, 9, 11, 15, 19, 23, 27, 31, 35]
+    assert one["phase"].tolist() == ["burnin"] * 3 + ["sampling"] * 7
+    assert one["a"].tolist()[:3] == raw["theta_burnin"][1, -1, :, 0].tolist()          # cold rung = last
+    assert one["loglikelihood"].tolist()[3:] == raw["loglike_sampling"][1, -1].tolist()
+
+
+def test_thin_argument_checks():
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
+    drj.use_builtin("example")
+    kw = dict(data={"x": np.ones(5)}, df_params=df, loglike="loglike", logprior="logprior", burnin=5, samples=5, silent=True)
+    with pytest.raises(ValueError):
+        drj.run_mcmc(thin=2, **kw)                       # needs output="summary"
+    with pytest.raises(ValueError):
+        drj.run_mcmc(thin=0, output="summary", **kw)
+    with pytest.raises(ValueError):
+        drj.run_mcmc(thin=2.5, output="summary", **kw)
