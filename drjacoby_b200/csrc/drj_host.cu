@@ -134,18 +134,22 @@ __global__ void __launch_bounds__(256) drj_chain_moments(const double* __restric
 
 // partial sums of (x_j - ctr)(x_{j+l} - ctr), l = l0 .. l0+15, over the chains CONCATENATED in chain order
 // (coda::effectiveSize is applied to the concatenated sampling draws, R/main.R:521-526).
-// grid = (nb, lag chunks of 16, parameters).  A CTA walks tiles of DRJ_AC_TILE consecutive elements of the
-// concatenated series: it stages x_j - ctr of the tile (xa) and of the tile shifted by l0 with a halo (xb) in
-// shared memory -- elements past the end are staged as 0, so the inner loop needs no bounds -- and every thread
-// takes PAIRS of consecutive j: one LDS.128 for (x_j, x_j+1), nine for the 18-value lag window, 32 DFMA into
-// 16 accumulators.  The first version read every operand from global memory (17 loads per 16 FMA and a 64-bit
-// division per element): 205 ms for 6.5e8 draws x 2 parameters x 89 lags, 60 % of the wall time of the ESS run.
+// grid = (parameters x lag chunks of 16, nb).  A CTA walks tiles of DRJ_AC_TILE consecutive elements of the
+// concatenated series: it stages x_j - ctr of the tile and of the tile shifted by l0 (+ halo) in shared memory
+// -- ONE run of TILE + l0 + HALO elements when l0 <= TILE; elements past the end are staged as 0, so the
+// inner loop needs no bounds -- and every thread takes EIGHT consecutive j against the 24-value lag window
+// they share: 4 + 12 LDS.128 for 128 DFMA into 16 accumulators (with pairs of j it was 10 LDS.128 per 32 DFMA
+// and shared-memory bound).  Layout in shared memory: 8 values, 2 pad (80-byte groups), so that the 16-byte
+// loads of the 8 lanes of a quarter-warp, 80 bytes apart, hit distinct banks.
+// History: v1 read every operand from global memory (17 loads per 16 FMA, a 64-bit division per element):
+// 205 ms for 6.5e8 draws x 2 parameters x 89 lags, 60 % of the wall time of the ESS run; v2 (pairs) 45 ms.
 #define DRJ_LAGCH 16
 #define DRJ_AC_TILE 2048
 #define DRJ_AC_HALO 32
+#define DRJ_AC_PHYS(i) ((i) + 2 * ((i) >> 3))
 __device__ __forceinline__ void drj_ac_stage(double* __restrict__ dst, int count, const double* __restrict__ src, long long cs,
                                              long long ts, int S, long long N, long long j_first, double ctr) {
-  // dst[i] = x_{j_first + i} - ctr (0 past the end); one division per thread, then a carried (chain, t) walk.
+  // dst[phys(i)] = x_{j_first + i} - ctr (0 past the end); one division per thread, then a carried (chain, t) walk.
   // Eight loads are issued before the first store: one load in flight per warp left the kernel latency-bound.
   long long j = j_first + threadIdx.x;
   long long c = j / S;
@@ -162,52 +166,55 @@ __device__ __forceinline__ void drj_ac_stage(double* __restrict__ dst, int count
       if (t >= S) { t -= S; ++c; }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (i0 + u * (int)blockDim.x < count) dst[i0 + u * blockDim.x] = v[u] - ctr;
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * (int)blockDim.x;
+      if (i < count) dst[DRJ_AC_PHYS(i)] = v[u] - ctr;
+    }
   }
 }
 __global__ void __launch_bounds__(256) drj_autocov_partial(const double* __restrict__ src, long long cs, long long ts, int S,
-                                                          long long N, const double* __restrict__ ctrs, long long ntiles,
-                                                          double* __restrict__ partial /*[param][chunk][gridDim.x][DRJ_LAGCH]*/) {
+                                                          long long N, const double* __restrict__ ctrs, long long ntiles, int nchunk,
+                                                          double* __restrict__ partial /*[param][chunk][gridDim.y][DRJ_LAGCH]*/) {
   __shared__ double sh[8];
-  // xa = the tile, xb = the tile shifted by l0 (+ halo).  For l0 <= TILE they overlap and are staged as ONE
-  // run of TILE + l0 + HALO elements (staging is the larger half of this kernel's L2->SM traffic).
-  __shared__ __align__(16) double xs[2 * DRJ_AC_TILE + DRJ_AC_HALO];
-  const int chunk = blockIdx.y, k = blockIdx.z;
+  __shared__ __align__(16) double xs[DRJ_AC_PHYS(2 * DRJ_AC_TILE + DRJ_AC_HALO) + 2];
+  // blockIdx.x = (parameter, lag chunk), blockIdx.y = tile walker: the CTAs that stage the SAME tiles (one per
+  // chunk and parameter) are neighbours in launch order and walk in step, so the tile comes from HBM once and
+  // from L2 for the others
+  const int chunk = blockIdx.x % nchunk, k = blockIdx.x / nchunk;
   const int l0 = chunk * DRJ_LAGCH;
   const double ctr = ctrs[k];
   const double* x = src + k;
   const bool overlap = l0 <= DRJ_AC_TILE;
-  const double* const xa = xs;
-  const double* const xb = overlap ? xs + l0 : xs + DRJ_AC_TILE;
+  const int shift = overlap ? l0 : DRJ_AC_TILE;  // logical index of the shifted tile inside xs (a multiple of 8)
   double acc[DRJ_LAGCH];
 #pragma unroll
   for (int q = 0; q < DRJ_LAGCH; ++q) acc[q] = 0.0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (long long tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
     const long long j0 = tile * DRJ_AC_TILE;
     __syncthreads();
     if (overlap) drj_ac_stage(xs, DRJ_AC_TILE + l0 + DRJ_AC_HALO, x, cs, ts, S, N, j0, ctr);
     else {
       drj_ac_stage(xs, DRJ_AC_TILE, x, cs, ts, S, N, j0, ctr);
-      drj_ac_stage(xs + DRJ_AC_TILE, DRJ_AC_TILE + DRJ_AC_HALO, x, cs, ts, S, N, j0 + l0, ctr);
+      drj_ac_stage(xs + DRJ_AC_PHYS(DRJ_AC_TILE), DRJ_AC_TILE + DRJ_AC_HALO, x, cs, ts, S, N, j0 + l0, ctr);
     }
     __syncthreads();
-    for (int pr = threadIdx.x; pr < DRJ_AC_TILE / 2; pr += blockDim.x) {
-      const double2 xj = *reinterpret_cast<const double2*>(&xa[2 * pr]);
-      double w[DRJ_LAGCH + 2];
+    for (int it = threadIdx.x; it < DRJ_AC_TILE / 8; it += blockDim.x) {
+      const double2* pa = reinterpret_cast<const double2*>(&xs[10 * it]);
+      const double2* pw = reinterpret_cast<const double2*>(&xs[10 * (it + (shift >> 3))]);
+      double xj[8], w[24];
 #pragma unroll
-      for (int q = 0; q < DRJ_LAGCH + 2; q += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(&xb[2 * pr + q]);
-        w[q] = v.x; w[q + 1] = v.y;
-      }
+      for (int u = 0; u < 4; ++u) { const double2 v = pa[u]; xj[2 * u] = v.x; xj[2 * u + 1] = v.y; }
 #pragma unroll
-      for (int q = 0; q < DRJ_LAGCH; ++q) {
-        acc[q] = fma(xj.x, w[q], acc[q]);
-        acc[q] = fma(xj.y, w[q + 1], acc[q]);
-      }
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const double2 v = pw[5 * g + u]; w[8 * g + 2 * u] = v.x; w[8 * g + 2 * u + 1] = v.y; }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+        for (int q = 0; q < DRJ_LAGCH; ++q) acc[q] = fma(xj[jj], w[jj + q], acc[q]);
     }
   }
-  double* out = partial + (((long long)k * gridDim.y + chunk) * gridDim.x + blockIdx.x) * DRJ_LAGCH;
+  double* out = partial + (((long long)k * nchunk + chunk) * gridDim.y + blockIdx.y) * DRJ_LAGCH;
 #pragma unroll
   for (int q = 0; q < DRJ_LAGCH; ++q) {
     const double t = drj_block_sum(acc[q], sh);
@@ -1279,10 +1286,10 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
       else { double t = 0.0; for (int c = 0; c < C; ++c) t += mean[(size_t)c * D + k]; ctr[k] = t / C; }
     }
     SUM_TRY(cudaMemcpyAsync(d_ctr, ctr.data(), sizeof(double) * (size_t)D, cudaMemcpyHostToDevice, s->stream));
-    for (int k0 = 0; k0 < D; k0 += 65535) {  // grid.z limit
+    for (int k0 = 0; k0 < D; k0 += 65535) {
       const int nk = std::min(D - k0, 65535);
-      drj_autocov_partial<<<dim3(nb, nchunk, nk), 256, 0, s->stream>>>(th + k0, th_cs, th_ts, S, N, d_ctr + k0, ntiles,
-                                                                       d_part + (size_t)k0 * nchunk * nb * DRJ_LAGCH);
+      drj_autocov_partial<<<dim3(nchunk * nk, nb), 256, 0, s->stream>>>(th + k0, th_cs, th_ts, S, N, d_ctr + k0, ntiles, nchunk,
+                                                                        d_part + (size_t)k0 * nchunk * nb * DRJ_LAGCH);
       drj_reduce_partials<<<dim3(nchunk, nk), 32, 0, s->stream>>>(d_part + (size_t)k0 * nchunk * nb * DRJ_LAGCH, nb,
                                                                   d_ac + (size_t)k0 * (L + 1), L);
       s->aux_launches += 2;
