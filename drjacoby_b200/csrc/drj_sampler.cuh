@@ -195,7 +195,7 @@ __device__ __forceinline__ double* drj_tile_buf() {
                                // CTA barrier, refill) is a ~700-cycle dependent chain, 16 KB tiles left it dominant
 #define DRJ_TEAM_MAXSTAGES 12  // TEAM kernels: at most this many tiles in flight per CTA
 #define DRJ_TEAM_VRANKS 16     // TEAM kernels: canonical number of partial sums a data item is split into
-#define DRJ_TEAM_MAXR 32       // TEAM kernels: at most this many rungs
+#define DRJ_TEAM_MAXR 64       // TEAM kernels: at most this many rungs (sizes the all-gather buffer: 2 x 16 x MAXR doubles)
 #ifndef DRJ_TEAM_NT
 #define DRJ_TEAM_NT 256        // TEAM kernels: threads per CTA (512, at a 128-register cap, measured 5-10 % slower on every shape)
 #endif

@@ -95,7 +95,7 @@ typedef struct drj_config {
 #define DRJ_FLAG_NO_TMA 1    /* stage data tiles with plain loads instead of the TMA bulk-copy engine */
 #define DRJ_FLAG_STREAM_KERNEL 2   /* force the sweep-kernel variant that parks particle state in HBM across data sweeps */
 #define DRJ_FLAG_RESIDENT_KERNEL 4 /* force the variant that keeps particle state in registers (default unless data is streamed) */
-#define DRJ_FLAG_TEAM_KERNEL 8      /* force the cluster-per-chain kernels (few chains x long data; datum-form models, rungs <= 32) */
+#define DRJ_FLAG_TEAM_KERNEL 8      /* force the cluster-per-chain kernels (few chains x long data; datum-form models, rungs <= 64) */
 #define DRJ_FLAG_NO_TEAM_KERNEL 16  /* never use the cluster-per-chain kernels */
 
 /* A model = the user's loglike + logprior (inst/templates/cpp_template.cpp:4-18).  Either a

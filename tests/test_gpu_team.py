@@ -40,9 +40,12 @@ TEAM_CASES = {
     # 3 rungs: 85 slots, one left-over thread
     "rungs3_hot": Case("example", [-10, 0], [10, np.inf], data=[normal_data(6001)], beta=beta_ladder(3, 2.0), chains=5,
                        burnin=10, samples=10, save_hot_draws=True),
-    # the maximum of 32 rungs, fewer tiles (3) than virtual ranks
+    # 32 rungs, fewer tiles (1) than virtual ranks
     "rungs32": Case("example", [-10, 0], [10, np.inf], data=[normal_data(5000)], beta=beta_ladder(32), chains=2,
                     burnin=8, samples=8),
+    # more rungs than a warp: 5 slots of 50 rungs, 6 left-over threads
+    "rungs50": Case("example", [-10, 0], [10, np.inf], data=[normal_data(20011)], beta=beta_ladder(50, 3.0), chains=2,
+                    burnin=6, samples=6),
     "normal_mu": Case("normal_mu", [-np.inf], [np.inf], data=[normal_data(33333)], chains=4, burnin=10, samples=10),
 }
 
