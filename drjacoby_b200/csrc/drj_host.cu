@@ -1333,7 +1333,8 @@ static int copy_series(drj_session* s, double* dst, const double* src, long long
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148 * 16));
   drj_thin_rows<<<grid, 256, 0, s->stream>>>(src, tmp, n_series, n, n_keep, w, thin);
   s->aux_launches++;
-  cudaError_t e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
   cudaFree(tmp);
   CUDA_TRY(e);
