@@ -282,12 +282,14 @@ struct drj_model {
   bool datum_form = false;
   bool jit = false;
   const void* init_fn = nullptr;   // built-in: __global__ function addresses
+  const void* init_chain_fn = nullptr;  // initial likelihood / prior, one thread per chain
   const void* sweep_fn = nullptr;
   const void* stream_fn = nullptr; // sweep variant for data streamed through shared memory (datum-form models)
   const void* team_init_fn = nullptr;   // cluster-per-chain variants (datum-form models)
   const void* team_sweep_fn = nullptr;
   CUmodule module = nullptr;       // jit
-  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr;
+  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr,
+             init_chain_cu = nullptr;
   double compile_seconds = 0.0;
   int device = 0;
 };
@@ -301,6 +303,7 @@ struct BuiltinEntry {
   const void* stream_fn;
   const void* team_init_fn;
   const void* team_sweep_fn;
+  const void* init_chain_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
@@ -308,7 +311,7 @@ struct BuiltinEntry {
     NAME, __VA_ARGS__::D, __VA_ARGS__::NBLOCK, __VA_ARGS__::DATUM_FORM,                  \
         (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__, false>, \
         DrjStreamKernel<__VA_ARGS__>::get(), DrjStreamKernel<__VA_ARGS__>::team_init(),                \
-        DrjStreamKernel<__VA_ARGS__>::team_sweep()                                                     \
+        DrjStreamKernel<__VA_ARGS__>::team_sweep(), (const void*)drj_init_chain_kernel<__VA_ARGS__>    \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -478,6 +481,9 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init(const __grid_constant__ DrjKernelArgs a) {\n"
        "  drj_init_body<DRJ_USER_MODEL, false>(a);\n"
        "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init_chain(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  drj_init_chain_body<DRJ_USER_MODEL>(a);\n"
+       "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
        "  drj_sweep_body<DRJ_USER_MODEL, false, false>(a);\n"
        "}\n"
@@ -497,7 +503,7 @@ static std::string make_jit_source(const drj_model_desc* desc) {
 static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
   const double t0 = wall_now();
   const std::string src = make_jit_source(desc);
-  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v3";
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v5";
   char hex[32];
   snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)fnv1a(key_text));
   const std::string path = cache_dir() + "/" + hex + ".cubin";
@@ -554,7 +560,8 @@ static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err)
       g_drv.ModuleGetFunction(&m->sweep_cu, m->module, "drj_user_sweep") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&m->stream_cu, m->module, "drj_user_sweep_stream") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&m->team_init_cu, m->module, "drj_user_init_team") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->team_sweep_cu, m->module, "drj_user_sweep_team") != CUDA_SUCCESS)
+      g_drv.ModuleGetFunction(&m->team_sweep_cu, m->module, "drj_user_sweep_team") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&m->init_chain_cu, m->module, "drj_user_init_chain") != CUDA_SUCCESS)
     return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
   {  // does the user's model use the per-datum form?
     CUfunction traits = nullptr;
@@ -594,7 +601,7 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       drj_model* m = new drj_model();
       m->name = b.name; m->D = b.D; m->NBLOCK = b.NBLOCK; m->datum_form = b.datum_form;
       m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->stream_fn = b.stream_fn; m->device = device;
-      m->team_init_fn = b.team_init_fn; m->team_sweep_fn = b.team_sweep_fn;
+      m->team_init_fn = b.team_init_fn; m->team_sweep_fn = b.team_sweep_fn; m->init_chain_fn = b.init_chain_fn;
       *out = m;
       return DRJ_OK;
     }
@@ -735,6 +742,26 @@ static cudaError_t upload_list(drj_session* s, const drj_list* l, DrjList* out) 
   e = cudaStreamSynchronize(s->stream);
   out->values = vals; out->offsets = doff; out->lengths = dlen; out->n_items = n;
   return e;
+}
+
+// initial likelihood and prior, one thread per chain (not for the cluster kernels, whose init kernel does it itself)
+static int launch_init_chain(drj_session* s, drj_error* err) {
+  const drj_model* m = s->model;
+  void* params[] = {(void*)&s->a};
+  const unsigned threads = (unsigned)std::min(128, ((s->C + 31) / 32) * 32);
+  const unsigned grid = (unsigned)((s->C + threads - 1) / threads);
+  if (m->jit) {
+    CUresult cr = g_drv.LaunchKernel(m->init_chain_cu, grid, 1, 1, threads, 1, 1, s->dyn_smem, (CUstream)s->stream, params, nullptr);
+    if (cr != CUDA_SUCCESS) {
+      const char* es = nullptr;
+      g_drv.GetErrorString(cr, &es);
+      return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernel: %s", es ? es : "?");
+    }
+  } else {
+    CUDA_TRY(cudaLaunchKernel(m->init_chain_fn, dim3(grid), dim3(threads), params, s->dyn_smem, s->stream));
+  }
+  s->aux_launches++;
+  return DRJ_OK;
 }
 
 static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
@@ -1141,7 +1168,11 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
 
   // ---- Particle::init + init_like for every chain x rung, row 0 of the burn-in outputs
   a.n_iter = 1; a.iter0 = 0;
-  int rc = launch_model_kernel(s, false, err);
+  CUDA_TRY(dalloc(s, &a.init_llb, (size_t)B * C));
+  CUDA_TRY(dalloc(s, &a.init_lp, (size_t)C));
+  int rc = s->team ? DRJ_OK : launch_init_chain(s, err);
+  if (rc) return rc;
+  rc = launch_model_kernel(s, false, err);
   if (rc) return rc;
   s->aux_launches++;
   if ((rc = flush_ring(s, 1, false, 0, err))) return rc;

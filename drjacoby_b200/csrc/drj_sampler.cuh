@@ -92,6 +92,9 @@ struct DrjKernelArgs {
   double* ring_ll;    // [n_iter][P] or [n_iter][chains]
   double* ring_lp;
   double* ring_theta; // [n_iter][D][P] or [n_iter][D][chains]
+  // initial block likelihoods / prior of every chain (all rungs of a chain start from the same theta)
+  double* init_llb;   // [B][chains]
+  double* init_lp;    // [chains]
   // error slot
   unsigned long long* err_key;  // packed (iteration-in-launch, chain, rung, param), atomicMin
   int* err_code;                // [P] code of the particle's first error in this launch
@@ -579,6 +582,44 @@ __device__ __forceinline__ void drj_store_state(const DrjKernelArgs& a, const Dr
 // ------------------------------------------------------------------ init kernel body
 // Particle::init + theta_to_phi + init_like for every (chain, rung); writes state and row 0 of the
 // burn-in outputs (main.cpp:128-137).
+// Particle::init_like (Particle.h:59-79), ONE thread per chain: every rung of a chain starts from the same
+// theta (R/main.R:322-328, one init column per chain), so the initial block likelihoods and the prior are the
+// same for all of them -- the reference evaluates them once per rung, here once per chain (identical values:
+// same inputs, same arithmetic).  With 32 rungs and n = 1e7 this takes the initial sweep from 470 ms to ~25 ms.
+// The particle-level init kernel (drj_init_body) then reads them.
+template <class M>
+__device__ __forceinline__ void drj_init_chain_body(const DrjKernelArgs& a) {
+  constexpr int D = M::D, B = M::NBLOCK;
+  constexpr int UB = DRJ_UNROLL_N(B);
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = c < a.chains;
+  const long long cc = active ? c : 0;  // inactive threads shadow chain 0 (uniform control flow)
+  DrjTiles<M> T;
+  T.template init<false>(a);
+  double theta[D], llb[B];
+  for (int i = 0; i < D; ++i) theta[i] = a.theta_init[cc * D + i];
+#pragma unroll UB
+  for (int b = 0; b < B; ++b) llb[b] = 0.0;
+  // every block listed by every parameter (Particle.h:62-68); a block listed by several parameters is
+  // evaluated once: same theta, same value
+  unsigned long long seen = 0ULL;
+  for (int i = 0; i < D; ++i)
+    for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+      const int b = a.block_idx[j];
+      if (b <= 64) {
+        if ((seen >> (b - 1)) & 1ULL) continue;
+        seen |= 1ULL << (b - 1);
+      }
+      llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, false>(T, a, theta, b);
+    }
+  const double lp = M::logprior(theta, a.misc);
+  if (active) {
+#pragma unroll UB
+    for (int b = 0; b < B; ++b) a.init_llb[(long long)b * a.chains + c] = llb[b];
+    a.init_lp[c] = lp;
+  }
+}
+
 // TEAM: one cluster per chain, every thread a replica of rung (tid mod R); the replica in slot 0 of CTA 0
 // of the cluster (`active`) is the one that writes to HBM.
 template <class M, bool TEAM>
@@ -595,7 +636,7 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
   const long long P = a.P;
 
   DrjTiles<M> T;
-  T.template init<TEAM>(a);
+  if constexpr (TEAM) T.template init<TEAM>(a);
 
   DrjState<M> s;
   int err = 0;
@@ -618,22 +659,29 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
   }
 #pragma unroll UB
   for (int b = 0; b < B; ++b) s.llb[b] = 0.0;
-  // init_like: every block listed by every parameter (duplicates re-evaluated), Particle.h:62-68
-  // (a block listed by several parameters is evaluated once: same theta, same value)
-  unsigned long long seen = 0ULL;
-  for (int i = 0; i < D; ++i)
-    for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
-      const int b = a.block_idx[j];
-      if (b <= 64) {
-        if ((seen >> (b - 1)) & 1ULL) continue;
-        seen |= 1ULL << (b - 1);
+  if constexpr (TEAM) {
+    // init_like: every block listed by every parameter (duplicates re-evaluated), Particle.h:62-68
+    // (a block listed by several parameters is evaluated once: same theta, same value)
+    unsigned long long seen = 0ULL;
+    for (int i = 0; i < D; ++i)
+      for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+        const int b = a.block_idx[j];
+        if (b <= 64) {
+          if ((seen >> (b - 1)) & 1ULL) continue;
+          seen |= 1ULL << (b - 1);
+        }
+        s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, TEAM>(T, a, s.theta, b);
       }
-      s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, TEAM>(T, a, s.theta, b);
-    }
+    s.lp = M::logprior(s.theta, a.misc);
+  } else {
+    // evaluated once per chain by drj_init_chain_body (all rungs of a chain start from the same theta)
+#pragma unroll UB
+    for (int b = 0; b < B; ++b) s.llb[b] = a.init_llb[(long long)b * a.chains + cc];
+    s.lp = a.init_lp[cc];
+  }
   s.ll = 0.0;
 #pragma unroll UB
   for (int b = 0; b < B; ++b) s.ll += s.llb[b];
-  s.lp = M::logprior(s.theta, a.misc);
   if (err == 0 && (s.ll == -DRJ_INF || s.lp == -DRJ_INF)) err = DRJ_ERR_INIT_NEGINF;
 
   if (active) {
@@ -955,6 +1003,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 template <class M>
 __global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant__ DrjKernelArgs a) {
   drj_init_body<M, false>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT) drj_init_chain_kernel(const __grid_constant__ DrjKernelArgs a) {
+  drj_init_chain_body<M>(a);
 }
 template <class M, bool STREAM>
 __global__ void __launch_bounds__(DRJ_NT, (STREAM ? 2 : DRJ_MINB)) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
