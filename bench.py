@@ -424,7 +424,7 @@ def main():
     ap.add_argument("--n-data", type=int, default=N_DATA)
     ap.add_argument("--chains-per-gpu", type=int, default=CHAINS_PER_GPU)
     ap.add_argument("--e2e-iters", type=int, default=4)
-    ap.add_argument("--e2e-calls", type=int, default=1)
+    ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--cpu-iters", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweeps", action="store_true")
