@@ -95,6 +95,7 @@ SYMBOLS = {
     "drj_session_advance": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(DrjError)]),
     "drj_session_iterations_done": (C.c_int, [C.c_void_p]),
     "drj_session_download": (C.c_int, [C.c_void_p, C.POINTER(DrjOutput), C.POINTER(DrjError)]),
+    "drj_release_cached_memory": (C.c_int64, []),
     "drj_session_download_thinned": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DrjOutput), C.POINTER(DrjError)]),
     "drj_session_summary": (C.c_int, [C.c_void_p, C.POINTER(DrjSummary), C.POINTER(DrjError)]),
     "drj_session_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

@@ -469,17 +469,23 @@ def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, worl
             t = torch.from_numpy(ac).to(devc)
             dist.all_reduce(t)
             ac = t.cpu().numpy()
-            # lag products that straddle two ranks' shards: tail of rank k x head of rank k+1
-            ends = gather_shards({"head": second["head"][None], "tail": second["tail"][None]}, chains, rank, world)
-            if rank == 0 and max_lag > 0:
+        raw = sess.download(draws=False) if thin is None else sess.download(draws=True, thin=thin)
+        if world > 1:
+            # one gather for the counters and for each shard's first / last max_lag draws
+            both = gather_shards(dict(raw, _head=second["head"][None], _tail=second["tail"][None]), chains, rank, world)
+            if rank == 0:
+                hd_all, tl_all = both.pop("_head"), both.pop("_tail")
+                raw = both
+                # lag products that straddle two ranks' shards: tail of rank k x head of rank k+1
                 for k in range(world - 1):
-                    tl, hd = ends["tail"][k] - center[:, None], ends["head"][k + 1] - center[:, None]   # [d, L]
+                    if max_lag <= 0:
+                        break
+                    tl, hd = tl_all[k] - center[:, None], hd_all[k + 1] - center[:, None]   # [d, L]
                     for lag in range(1, max_lag + 1):
                         # x_j in the last `lag` draws of shard k pairs with x_{j+lag} among the first `lag` of shard k+1
                         ac[:, lag] += (tl[:, max_lag - lag:] * hd[:, :lag]).sum(axis=1)
-        raw = sess.download(draws=False) if thin is None else sess.download(draws=True, thin=thin)
-        if world > 1:
-            raw = gather_shards(raw, chains, rank, world)
+            else:
+                raw = None
     finally:
         sess.close()
     if rank != 0:
@@ -531,28 +537,65 @@ def shard_range(chains: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_PACK_LIMIT = 8 << 20  # arrays up to this many bytes per rank travel packed in one message
+
+
 def gather_shards(raw: dict, chains: int, rank: int, world: int) -> dict | None:
     """End-of-run gather of every rank's chain slice to rank 0 (NCCL when the ranks own GPUs, gloo on
-    CPU): the only collective of a run, never on the sampling hot path."""
+    CPU): the only collective of a run, never on the sampling hot path.  One metadata exchange for all
+    arrays; the small ones (counters, per-chain summaries) are packed into a single message per rank, the
+    large ones (draws) are sent one by one."""
     import torch
     import torch.distributed as dist
     backend = dist.get_backend()
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    keys = sorted(raw)
+    arrs = {k: np.ascontiguousarray(raw[k]) for k in keys}
+    meta = {k: (tuple(arrs[k].shape), arrs[k].dtype.str) for k in keys}
+    all_meta = [None] * world
+    dist.all_gather_object(all_meta, meta)
+
+    def nbytes(m):
+        return int(np.prod(m[0], dtype=np.int64)) * np.dtype(m[1]).itemsize
+
+    small = [k for k in keys if max(nbytes(all_meta[r][k]) for r in range(world)) <= _PACK_LIMIT]
+    large = [k for k in keys if k not in small]
     out = {} if rank == 0 else None
-    for key in sorted(raw):
-        a = np.ascontiguousarray(raw[key])
-        t = torch.from_numpy(a).to(dev)
-        shapes = [None] * world
-        dist.all_gather_object(shapes, tuple(a.shape))
+    if small:
+        sizes = [sum(nbytes(all_meta[r][k]) for k in small) for r in range(world)]
+        width = max(max(sizes), 1)
+        mine = np.zeros(width, dtype=np.uint8)
+        off = 0
+        for k in small:
+            b = arrs[k].view(np.uint8).reshape(-1)
+            mine[off:off + b.size] = b
+            off += b.size
+        t = torch.from_numpy(mine).to(dev)
         if rank == 0:
-            parts = [t] + [torch.empty(shapes[r], dtype=t.dtype, device=dev) for r in range(1, world)]
+            got = [torch.empty(width, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.gather(t, got, dst=0)
+            host = [g.cpu().numpy() for g in got]
+            offs = [0] * world
+            for k in small:
+                parts = []
+                for r in range(world):
+                    shp, dt = all_meta[r][k]
+                    n = nbytes(all_meta[r][k])
+                    parts.append(host[r][offs[r]:offs[r] + n].view(np.dtype(dt)).reshape(shp))
+                    offs[r] += n
+                out[k] = np.concatenate(parts, axis=0)
+        else:
+            dist.gather(t, dst=0)
+    for k in large:
+        t = torch.from_numpy(arrs[k]).to(dev)
+        if rank == 0:
+            parts = [t] + [torch.empty(all_meta[r][k][0], dtype=t.dtype, device=dev) for r in range(1, world)]
             for r in range(1, world):
                 if parts[r].numel():
                     dist.recv(parts[r], src=r)
-            out[key] = torch.cat([p.reshape(shapes[i]) for i, p in enumerate(parts)], dim=0).cpu().numpy()
+            out[k] = torch.cat(parts, dim=0).cpu().numpy()
         elif t.numel():
             dist.send(t, dst=0)
-    dist.barrier()
     return out
 
 

@@ -645,6 +645,84 @@ extern "C" double drj_model_compile_seconds(const drj_model* m) { return m ? m->
 // ------------------------------------------------------------------------------------------------
 // session
 // ------------------------------------------------------------------------------------------------
+// ---- device-memory pool.  A session's buffers (tens of GB of stored draws for a long run) go back to a
+// process-wide pool when the session is destroyed and are handed to the next session that asks for the same
+// size, instead of cudaFree / cudaMalloc: a series of runs of one shape (the usual way run_mcmc is used, and
+// what bench.py does) then costs no allocation time, and -- measured -- the memory-bound summary kernels of the
+// next run no longer slow down several-fold now and then right after tens of GB were freed and re-allocated.
+// Blocks >= 1 MB only, at most DRJ_POOL_GB (default 48) GB per process, everything is released when an
+// allocation fails or drj_release_cached_memory() is called.
+struct PoolBlock { void* p; size_t bytes; int device; };
+static std::vector<PoolBlock> g_pool;
+static size_t g_pool_bytes = 0;
+static std::mutex g_pool_mutex;
+
+static size_t pool_cap() {
+  static size_t cap = [] {
+    const char* e = getenv("DRJ_POOL_GB");
+    const double gb = e ? atof(e) : 48.0;
+    return gb > 0 ? (size_t)(gb * 1073741824.0) : (size_t)0;
+  }();
+  return cap;
+}
+static size_t pool_release(int device) {  // device < 0: all devices
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  size_t freed = 0;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (size_t i = 0; i < g_pool.size();) {
+    if (device < 0 || g_pool[i].device == device) {
+      cudaSetDevice(g_pool[i].device);
+      cudaFree(g_pool[i].p);
+      freed += g_pool[i].bytes;
+      g_pool_bytes -= g_pool[i].bytes;
+      g_pool[i] = g_pool.back();
+      g_pool.pop_back();
+    } else ++i;
+  }
+  cudaSetDevice(cur);
+  return freed;
+}
+static size_t pool_cached(int device) {
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  size_t n = 0;
+  for (const PoolBlock& b : g_pool) if (b.device == device) n += b.bytes;
+  return n;
+}
+static cudaError_t pool_alloc(int device, size_t bytes, void** out) {
+  if (bytes >= (1u << 20)) {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (size_t i = 0; i < g_pool.size(); ++i)
+      if (g_pool[i].device == device && g_pool[i].bytes == bytes) {
+        *out = g_pool[i].p;
+        g_pool_bytes -= bytes;
+        g_pool[i] = g_pool.back();
+        g_pool.pop_back();
+        return cudaSuccess;
+      }
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {  // give the cached blocks back to the driver and try again
+    cudaGetLastError();
+    if (pool_release(device) > 0) e = cudaMalloc(out, bytes);
+  }
+  return e;
+}
+static void pool_free(int device, void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes >= (1u << 20)) {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    if (g_pool_bytes + bytes <= pool_cap()) {
+      g_pool.push_back({p, bytes, device});
+      g_pool_bytes += bytes;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
+extern "C" int64_t drj_release_cached_memory(void) { return (int64_t)pool_release(-1); }
+
 struct drj_session {
   drj_config cfg;
   const drj_model* model = nullptr;
@@ -652,7 +730,7 @@ struct drj_session {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   double sweep_ms_total = 0.0, stream_ms_total = 0.0;  // CUDA-event time: sweep kernels / sweep + transposes
   DrjKernelArgs a;
-  std::vector<void*> allocs;
+  std::vector<std::pair<void*, size_t>> allocs;  // device buffers of the session (returned to the pool on destroy)
   int D = 0, B = 0, R = 0, C = 0;
   long long P = 0, Ppt = 0, Pth = 0;
   int d_free = 0;
@@ -696,8 +774,9 @@ static cudaError_t scratch_get(drj_session* s, int slot, size_t bytes, double** 
 template <class T>
 static cudaError_t dalloc(drj_session* s, T** p, size_t n) {
   void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
-  if (e == cudaSuccess) { s->allocs.push_back(q); *p = (T*)q; }
+  const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  cudaError_t e = pool_alloc(s->cfg.device, bytes, &q);
+  if (e == cudaSuccess) { s->allocs.push_back({q, bytes}); *p = (T*)q; }
   return e;
 }
 
@@ -963,7 +1042,8 @@ static int validate(const drj_config* c, const drj_model* m, const drj_list* dat
 extern "C" void drj_session_destroy(drj_session* s) {
   if (!s) return;
   cudaSetDevice(s->cfg.device);
-  for (void* p : s->allocs) cudaFree(p);
+  cudaStreamSynchronize(s->stream);  // nothing of this session may still be running when its buffers are reused
+  for (auto& pb : s->allocs) pool_free(s->cfg.device, pb.first, pb.second);
   for (void* p : s->scratch) if (p) cudaFree(p);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1030,6 +1110,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
   const double need = bytes_final + bytes_state + bytes_replay + ring_row * tb + 64e6;
+  free_b += pool_cached(cfg->device);  // blocks in the library's own pool are reused or released on demand
   if (need > 0.92 * (double)free_b)
     return set_err(err, DRJ_ERR_MEMORY,
                    "run needs %.1f GB of device memory (outputs %.1f GB) but %.1f GB are free: reduce iterations, "

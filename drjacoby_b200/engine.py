@@ -298,6 +298,11 @@ class Session:
             pass
 
 
+def release_cached_memory() -> int:
+    """Give the device buffers the library keeps for reuse (drj_host.cu, memory pool) back to the driver."""
+    return int(L.lib().drj_release_cached_memory())
+
+
 def fp64_peak_tflops(device: int = 0) -> float:
     v = C.c_double(0)
     err = L.DrjError()

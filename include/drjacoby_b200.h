@@ -171,6 +171,10 @@ typedef struct drj_session drj_session; /* opaque */
 /* ---- library */
 int drj_abi_version(void);
 int drj_device_count(void);
+/* Device buffers of destroyed sessions are kept in a process-wide pool (at most DRJ_POOL_GB GB, default 48; 0 turns
+ * it off) and reused by the next session of the same shape; the pool is emptied when an allocation fails, or here.
+ * Returns the bytes given back to the driver.  (No reference counterpart: R's allocator is the host's.) */
+int64_t drj_release_cached_memory(void);
 int drj_builtin_model_count(void);
 const char* drj_builtin_model_name(int i);
 

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     text = open(os.path.join(ROOT, "include", "drjacoby_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"^\s*(?:int|void|double|const char\*)\s+(drj_[a-z0-9_]+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:int|void|double|int64_t|const char\*)\s+(drj_[a-z0-9_]+)\s*\(", text, flags=re.M)
     return sorted(set(names))
 
 

@@ -483,3 +483,27 @@ def test_summary_mode_with_thinned_draws():
     pd.testing.assert_frame_equal(thin.output, keep)
     with pytest.raises(ValueError):
         drj.run_mcmc(thin=10, **kw)
+
+
+def test_memory_pool_reuses_and_releases_session_buffers():
+    """Buffers of a destroyed session are reused by the next session of the same shape (same results, stale
+    contents never visible) and can be handed back to the driver."""
+    from drjacoby_b200 import engine
+    engine.release_cached_memory()
+    x = np.random.default_rng(5).normal(3, 2, 50)
+    def run(seed, chains=4096):
+        spec = engine.RunSpec(theta_min=[-10.0, 0.0], theta_max=[10.0, np.inf], theta_init=np.tile([3.0, 2.0], (chains, 1)), burnin=20,
+                              samples=40, rng_mode="philox", seed=seed, data=[x])
+        return engine.run_raw(engine.Model(builtin="example"), spec)
+    a1 = run(1)
+    b = run(2)           # same shape: reuses a1's buffers, different seed -> different contents
+    a2 = run(1)          # and again: must reproduce a1 exactly
+    for k in a1:
+        if k != "t_diff":
+            assert np.array_equal(a1[k], a2[k]), k
+    assert not np.array_equal(a1["theta_sampling"], b["theta_sampling"])
+    small = run(1, chains=8)   # a different shape next to cached blocks
+    assert np.array_equal(small["theta_sampling"], a1["theta_sampling"][:8])
+    freed = engine.release_cached_memory()
+    assert freed >= a1["theta_sampling"].nbytes   # at least the sampling draws were cached
+    assert engine.release_cached_memory() == 0
