@@ -57,3 +57,36 @@ def test_two_ranks_equal_one(tmp_path, oracle):
         if k != "t_diff":
             assert np.array_equal(got[k], v), k
     assert np.array_equal(got["rhat"], ref.diagnostics["rhat"].to_numpy())
+
+
+def _gather_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from drjacoby_b200 import api
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    api._PACK_LIMIT = 1000  # bytes: "big" travels on its own, the others in the packed message
+    n = 2 + rank            # uneven shards
+    rng = np.random.default_rng(rank)
+    raw = {"big": rng.normal(size=(n, 70, 3)), "counts": rng.integers(0, 9, size=(n, 4)).astype(np.int32), "empty": np.zeros((n, 0), np.int32),
+           "t": rng.normal(size=n)}
+    out = api.gather_shards(raw, 2 + 3 + 4, rank, world)
+    np.savez(os.path.join(tmpdir, f"in{rank}.npz"), **raw)
+    if rank == 0:
+        np.savez(os.path.join(tmpdir, "out.npz"), **out)
+    else:
+        assert out is None
+    dist.destroy_process_group()
+
+
+def test_gather_shards_packed_and_large_paths(tmp_path):
+    """gather_shards: small arrays of all dtypes in one packed message, large ones one by one, uneven shard sizes,
+    zero-width arrays; rank 0 gets the concatenation in rank order."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.start_processes(_gather_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True, start_method="spawn")
+    out = np.load(os.path.join(tmp_path, "out.npz"))
+    ins = [np.load(os.path.join(tmp_path, f"in{r}.npz")) for r in range(3)]
+    for k in ("big", "counts", "empty", "t"):
+        want = np.concatenate([i[k] for i in ins], axis=0)
+        assert out[k].dtype == want.dtype and np.array_equal(out[k], want), k
