@@ -32,7 +32,9 @@ __device__ double logprior(const double* params, const DrjList& misc) {
 // The functions above are evaluated by ONE GPU thread per chain x rung, which walks all the data
 // itself.  If instead you describe ONE term of the sum, the sampler stages the data once per thread
 // block in shared memory (streamed by the TMA engine when it does not fit) and all chains x rungs of
-// the block walk it together.  Define a struct like this and `#define DRJ_USER_MODEL` to its name
+// the block walk it together; and when a run has only a few chains (chains x rungs <= 4096) over a long
+// data vector, every chain gets a whole cluster of thread blocks that divides the sum (one thread per
+// chain x rung would take ~5 clock cycles per data point whatever the GPU).  Define a struct like this and `#define DRJ_USER_MODEL` to its name
 // (loglike()/logprior() above are then unused and may be deleted):
 //
 //   struct MyModel {
