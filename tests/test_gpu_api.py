@@ -507,3 +507,17 @@ def test_memory_pool_reuses_and_releases_session_buffers():
     freed = engine.release_cached_memory()
     assert freed >= a1["theta_sampling"].nbytes   # at least the sampling draws were cached
     assert engine.release_cached_memory() == 0
+
+
+def test_readme_usage_example_runs():
+    """The usage example of README.md, executed as written: posterior of the normal model around (3, 2)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "README.md")).read()
+    code = re.search(r"## Using it like the reference\s+```python\n(.*?)```", text, flags=re.S).group(1)
+    ns = {}
+    exec(code, ns)
+    m = ns["mcmc"]
+    s = m.output[m.output.phase == "sampling"]
+    assert len(s) == 5 * 10000 and abs(s["mu"].mean() - 3.0) < 0.6 and abs(s["sigma"].mean() - 2.0) < 0.6
+    assert m.diagnostics["rhat"]["mu"] < 1.05 and m.diagnostics["ess"]["mu"] > 1000
