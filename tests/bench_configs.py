@@ -1,6 +1,8 @@
 """Throughput of BASELINE.json's other configs (K1-K4) on one GPU next to the CPU oracle port.
-Not the headline bench (bench.py = K5); prints one JSON line per config.  Run on the GPU box:
-    python tools/bench_configs.py
+Not the headline bench (bench.py = K5); prints one JSON line per config.  It lives under tests/ because it times
+the CPU oracle as the baseline (oracle/ is test infrastructure: only tests/, smoke() and bench.py may load it).
+Run on the GPU box:
+    python tests/bench_configs.py
 """
 import json
 import os
@@ -11,7 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # helpers
 import drjacoby_b200 as drj  # noqa: E402
 from helpers import Case, POPULATION, beta_ladder, gpu_spec, run_oracle  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
