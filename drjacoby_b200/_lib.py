@@ -154,7 +154,10 @@ def make_list(items, names=None):
     arrs = [np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel()) for a in items]
     lengths = np.array([a.size for a in arrs], dtype=np.int64)
     offsets = (np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64) if arrs else np.zeros(0, np.int64))
-    values = np.ascontiguousarray(np.concatenate(arrs) if arrs and lengths.sum() > 0 else np.zeros(1), dtype=np.float64)
+    if len(arrs) == 1 and arrs[0].size > 0:
+        values = arrs[0]  # no copy: a caller's pinned buffer goes to the device as it is
+    else:
+        values = np.ascontiguousarray(np.concatenate(arrs) if arrs and lengths.sum() > 0 else np.zeros(1), dtype=np.float64)
     cnames = None
     if names is not None and len(arrs):
         cnames = (C.c_char_p * len(arrs))(*[str(n).encode() for n in names])
