@@ -163,12 +163,14 @@ def ess_sweep(drj, device, rank, world, barrier):
     run_mcmc(output="summary", cluster="torch") shards the chains over the ranks, reduces the draws on each
     device (drj_session_summary) and merges moments and autocovariance sums over NCCL -- exactly the ESS of
     the concatenated run, the 7.2e8 draws per GPU never move.  Called by every rank; wall = max over ranks.
-A tiny untimed call first sets up the NCCL point-to-point connections the gather uses."""
+One untimed call of the same shape first (NCCL set-up, first allocation of the stored draws)."""
     x = synth_data(100)
     chains, samples = ESS_CHAINS_PER_GPU * world, 10000
     df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", 0, "max", np.inf)
     drj.use_builtin("example")
-    drj.run_mcmc(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=10, samples=20, chains=2 * world, seed=3,
+    # untimed warm-up: the same call once (NCCL point-to-point set-up; the first allocation of the 23 GB of stored draws
+    # per GPU, which later runs take from the library's pool)
+    drj.run_mcmc(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=1000, samples=samples, chains=chains, seed=3,
                  silent=True, output="summary", cluster="torch" if world > 1 else None, device=device)
     walls = []
     for _ in range(2):  # the run is ~0.2 s; now and then one is several times slower (summary kernels, memory-bound, right
