@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libdrjacoby_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status codes (include/drjacoby_b200.h)
 OK = 0
@@ -22,6 +22,7 @@ ERR_ARG, ERR_MODEL, ERR_COMPILE, ERR_CUDA, ERR_MEMORY, ERR_INTERRUPT = 10, 11, 1
 RNG_PHILOX, RNG_REPLAY = 0, 1
 FLAG_NO_TMA, FLAG_STREAM_KERNEL, FLAG_RESIDENT_KERNEL = 1, 2, 4
 FLAG_TEAM_KERNEL, FLAG_NO_TEAM_KERNEL = 8, 16
+FLAG_GRID_KERNEL, FLAG_NO_GRID_KERNEL = 32, 64
 
 
 class DrjList(C.Structure):
@@ -41,7 +42,7 @@ class DrjConfig(C.Structure):
         ("beta_raised", C.POINTER(C.c_double)), ("theta_init", C.POINTER(C.c_double)),
         ("seed", C.c_uint64), ("chain_offset", C.c_int64), ("replay_uniforms", C.POINTER(C.c_double)),
         ("iters_per_launch", C.c_int32), ("chains_per_cta", C.c_int32), ("flags", C.c_int32),
-        ("reserved", C.c_int32),
+        ("layout_chains", C.c_int32),
     ]
 
 
@@ -66,10 +67,11 @@ class DrjOutput(C.Structure):
 
 
 class DrjSummary(C.Structure):
-    _fields_ = [("max_lag", C.c_int32), ("reserved", C.c_int32), ("center", C.POINTER(C.c_double)),
+    _fields_ = [("max_lag", C.c_int32), ("n_quantiles", C.c_int32), ("center", C.POINTER(C.c_double)),
                 ("chain_mean", C.POINTER(C.c_double)), ("chain_var", C.POINTER(C.c_double)),
                 ("autocov_sum", C.POINTER(C.c_double)), ("deviance_mean_var", C.POINTER(C.c_double)),
-                ("head", C.POINTER(C.c_double)), ("tail", C.POINTER(C.c_double))]
+                ("head", C.POINTER(C.c_double)), ("tail", C.POINTER(C.c_double)),
+                ("quantile_probs", C.POINTER(C.c_double)), ("quantiles", C.POINTER(C.c_double))]
 
 
 class DrjError(C.Structure):
@@ -102,6 +104,16 @@ SYMBOLS = {
     "drj_session_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "drj_session_destroy": (None, [C.c_void_p]),
     "drj_fp64_peak_tflops": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(DrjError)]),
+    "drj_run_mcmc_multi": (C.c_int, [C.POINTER(DrjConfig), C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(DrjList),
+                                     C.POINTER(DrjList), C.POINTER(DrjOutput), PROGRESS_FN, C.c_void_p, C.POINTER(DrjError)]),
+    "drj_multi_create": (C.c_int, [C.POINTER(DrjConfig), C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(DrjList),
+                                   C.POINTER(DrjList), C.POINTER(C.c_void_p), C.POINTER(DrjError)]),
+    "drj_multi_device_count": (C.c_int, [C.c_void_p]),
+    "drj_multi_advance": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(DrjError)]),
+    "drj_multi_download_thinned": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(DrjOutput), C.POINTER(DrjError)]),
+    "drj_multi_summary": (C.c_int, [C.c_void_p, C.POINTER(DrjSummary), C.POINTER(DrjError)]),
+    "drj_multi_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "drj_multi_destroy": (None, [C.c_void_p]),
 }
 
 _lib = None

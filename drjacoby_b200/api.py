@@ -186,13 +186,16 @@ def sample_chains(x: DrjacobyOutput, sample_n: int, keep_chain_index: bool = Fal
         raise TypeError("x must be a drjacoby_output")
     if sample_n < 1 or int(sample_n) != sample_n:
         raise ValueError("sample_n must be a positive integer")
+    if not isinstance(keep_chain_index, (bool, np.bool_)):
+        raise TypeError("keep_chain_index must be a single logical")
     df = x.output[x.output["phase"] == "sampling"]
+    df = df.drop(columns=["iteration", "phase", "logprior", "loglikelihood"] + ([] if keep_chain_index else ["chain"]))
     if sample_n > len(df):
-        raise ValueError("sample_n is larger than the total number of sampling iterations")
-    idx = np.round(np.linspace(1, len(df), int(sample_n))).astype(int) - 1
-    out = df.iloc[idx].drop(columns=["phase", "iteration"] + ([] if keep_chain_index else ["chain"]))
-    out = out.reset_index(drop=True)
-    out.insert(0, "sample", np.arange(1, len(out) + 1))
+        raise ValueError(f"sample_n cannot exceed the total number of samples over all chains ({len(df)})")
+    # all_chains[seq.int(1, N, length.out = n), ]: R truncates fractional row indices
+    idx = np.floor(np.linspace(1, len(df), int(sample_n))).astype(int) - 1
+    out = df.iloc[idx].reset_index(drop=True)
+    out["sample"] = np.arange(1, len(out) + 1)
     return out
 
 
@@ -219,7 +222,8 @@ def _flatten_list(d: dict, what: str):
 def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3, samples=1e4, rungs=1, chains=5,
              beta_manual=None, alpha=1.0, target_acceptance=0.44, cluster=None, coupling_on=True, pb_markdown=False,
              save_data=True, save_hot_draws=False, silent=False, *, source: CudaSource | None = None, seed=None,
-             rng="philox", store_pt=True, device=None, as_frames=True, progress=None, output="full", thin=None) -> DrjacobyOutput:
+             rng="philox", store_pt=True, device=None, as_frames=True, progress=None, output="full", thin=None,
+             quantiles=None) -> DrjacobyOutput:
     """run_mcmc() of the reference (R/main.R:208-225) on the GPU.
 
     Extra keyword-only arguments: `source` (a CudaSource; default: the last source_cuda()/use_builtin()),
@@ -233,8 +237,13 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
     the device, as the usual `output` data frame with the original iteration numbers -- diagnostics stay exact (all
     draws, on the device), plots and quantiles work on the thinned frame (sample_chains() of the reference subsamples
     after the fact, R/samples.R; here the full set never has to leave the GPU).
-    `cluster`: None = this process's GPU; "torch" = shard chains over the ranks of an initialised
-    torch.distributed group (one process per GPU), results gathered on rank 0.
+    `quantiles` (with output="summary"): probabilities whose quantiles (R's quantile(), type 7) of every parameter's
+    cold-rung sampling draws are found on the device by a radix select -> diagnostics["quantiles"].
+    `cluster`: None = this process's GPU.  "gpus" (or a list of device ordinals) = ONE process, several GPUs: the chains
+    are split over the devices INSIDE the library (drj_run_mcmc_multi / drj_multi_*: one host thread per device, results
+    and summaries merged in C) -- what replaces the reference's PSOCK cluster (R/main.R:392-402) and what the R shim
+    calls.  "torch" = shard chains over the ranks of an initialised torch.distributed group (one process per GPU),
+    results gathered on rank 0.
     """
     t_start = time.perf_counter()
     # ---------- check inputs (R/main.R:236-283)
@@ -320,14 +329,22 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
 
     # ---------- sharding over ranks (cluster = "torch")
     rank, world = 0, 1
+    devices = None  # in-library multi-GPU: "all" or a list of ordinals
     if cluster is not None:
-        if cluster != "torch":
-            raise TypeError('cluster must be None or "torch" (torch.distributed ranks, one GPU each)')
-        import torch.distributed as dist
-        rank, world = dist.get_rank(), dist.get_world_size()
+        if isinstance(cluster, str) and cluster == "torch":
+            import torch.distributed as dist
+            rank, world = dist.get_rank(), dist.get_world_size()
+        elif isinstance(cluster, str) and cluster == "gpus":
+            devices = "all"
+        elif isinstance(cluster, (list, tuple)) and len(cluster) and all(isinstance(v, (int, np.integer)) for v in cluster):
+            devices = [int(v) for v in cluster]
+        else:
+            raise TypeError('cluster must be None, "gpus" / a list of CUDA device ordinals (one process, several GPUs), '
+                            'or "torch" (torch.distributed ranks, one GPU each)')
+    torch_cluster = cluster is not None and devices is None
     lo, hi = shard_range(chains, rank, world)
     if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if cluster is not None else 0
+        device = int(os.environ.get("LOCAL_RANK", "0")) if torch_cluster else 0
     T = burnin - 1 + samples
     d_free = int((~skip_param).sum())
     U = 3 * d_free * rungs + ((rungs - 1) if (coupling_on and rungs > 1) else 0)
@@ -336,19 +353,21 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
         # the reference runs chains one after another on one stream: chain c owns uniforms [c*T*U, (c+1)*T*U)
         allu = rstream.runif(chains * T * U)
         replay = allu[lo * T * U: hi * T * U]
+    # The kernel family (one thread per particle / one cluster per chain / the whole grid per run) and its reduction layout
+    # are chosen by the library from the WHOLE run's size (layout_chains), not the shard's: the families associate the
+    # likelihood sum differently (equal within 1e-10, not bitwise), so every shard -- and the same run on one GPU --
+    # must use the same one to stay bit-identical.
     flags = 0
-    if cluster is not None:
-        # the kernel family (one thread per particle / one cluster per chain) is chosen from the shard's size; the two
-        # associate the likelihood sum differently (equal within 1e-10, not bitwise).  Decide from the WHOLE run's size so
-        # that every shard -- and the same run on one GPU -- uses the same family and stays bit-identical.
-        longest = max([len(v) for v in data_items], default=0)
-        flags = _lib.FLAG_TEAM_KERNEL if (longest > 4096 and chains * rungs <= 4096) else _lib.FLAG_NO_TEAM_KERNEL
-    spec = engine.RunSpec(theta_min=tmin, theta_max=tmax, theta_init=init_mat.T[lo:hi], burnin=burnin, samples=samples,
-                          beta_raised=beta_raised, blocks=[list(b) for b in df_params["block"]], coupling_on=bool(coupling_on),
-                          save_hot_draws=bool(save_hot_draws), store_pt=bool(store_pt), target_acceptance=float(target_acceptance),
-                          rng_mode="replay" if rng == "r" else "philox", seed=0 if seed is None or rng == "r" else int(seed),
-                          chain_offset=lo, replay=replay, device=device, data=data_items, misc=misc_items,
-                          data_names=data_names, misc_names=misc_names, param_names=list(df_params["name"]), flags=flags)
+    spec = None  # more ranks than chains: this rank has no chains, but still enters every collective below
+    if hi > lo:
+        spec = engine.RunSpec(
+            theta_min=tmin, theta_max=tmax, theta_init=init_mat.T[lo:hi], burnin=burnin, samples=samples,
+            beta_raised=beta_raised, blocks=[list(b) for b in df_params["block"]], coupling_on=bool(coupling_on),
+            save_hot_draws=bool(save_hot_draws), store_pt=bool(store_pt), target_acceptance=float(target_acceptance),
+            rng_mode="replay" if rng == "r" else "philox", seed=0 if seed is None or rng == "r" else int(seed),
+            chain_offset=lo, replay=replay, device=device, data=data_items, misc=misc_items,
+            data_names=data_names, misc_names=misc_names, param_names=list(df_params["name"]), flags=flags,
+            layout_chains=chains)
 
     # ---------- run (one native call for all chains of this rank; R/main.R:392-402 loops chains instead)
     phase_names = ("burn-in", "sampling phase")
@@ -370,21 +389,30 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
         if int(thin) != thin or thin < 1:
             raise ValueError("thin must be a positive integer")
         thin = int(thin)
+    if quantiles is not None and output != "summary":
+        raise ValueError('quantiles= needs output="summary" (with output="full" the draws come back: use numpy / pandas quantile)')
     if output == "summary":
         raw, diagnostics = _run_summary(model, spec, _progress if not (silent and progress is None) else None, names=list(df_params["name"]),
-                                        skip_param=skip_param, chains=chains, rank=rank, world=world, beta_raised=beta_raised, thin=thin)
+                                        skip_param=skip_param, chains=chains, rank=rank, world=world, beta_raised=beta_raised, thin=thin,
+                                        devices=devices, quantiles=quantiles, shape=(burnin, samples, rungs, d, bool(save_hot_draws), bool(store_pt)))
         if rank != 0:
             return None
-        frame = None
+        frame = pt = None
         if thin is not None and as_frames:
-            frame = _thinned_frame(raw, list(df_params["name"]), burnin, samples, thin, chains)
+            frame, pt = _thinned_frames(raw, list(df_params["name"]), burnin, samples, thin, chains, rungs, bool(save_hot_draws))
         parameters = dict(data=data if save_data else None, df_params=df_params, loglike=loglike, logprior=logprior,
                           burnin=burnin, samples=samples, rungs=rungs, chains=chains, coupling_on=bool(coupling_on), alpha=alpha,
                           beta_manual=beta_manual)
         diagnostics["wall_seconds"] = time.perf_counter() - t_start
-        return DrjacobyOutput(frame, None, diagnostics, parameters, raw)
-    raw = _run_shard(model, spec, None if (silent and progress is None) else _progress)
-    if cluster is not None:
+        return DrjacobyOutput(frame, pt, diagnostics, parameters, raw)
+    cb = None if (silent and progress is None) else _progress
+    if devices is not None:
+        raw = engine.run_raw_multi(model, spec, None if devices == "all" else devices, cb)
+    elif spec is None:
+        raw = _empty_raw(burnin, samples, rungs, d, bool(save_hot_draws), bool(store_pt))
+    else:
+        raw = engine.run_raw(model, spec, cb)
+    if torch_cluster:
         raw = gather_shards(raw, chains, rank, world)
         if rank != 0:
             return None
@@ -409,110 +437,166 @@ def run_mcmc(data, df_params, misc=None, loglike=None, logprior=None, burnin=1e3
     return res
 
 
-def _thinned_frame(raw, names, burnin, samples, thin, chains):
-    """The `output` data frame (cold rung) from draws thinned on the device: stored iterations 0, thin, 2 thin, ... of
-    each phase, numbered as the reference numbers them (1..burnin, burnin+1..burnin+samples; R/main.R:420-476)."""
+def _empty_raw(burnin, samples, rungs, d, save_hot_draws, store_pt):
+    """The raw arrays of a shard with no chains (more ranks than chains): zero-length along the chain axis."""
+    ptR, thR = (rungs if store_pt else 1), (rungs if save_hot_draws else 1)
+    return dict(loglike_burnin=np.zeros((0, ptR, burnin)), logprior_burnin=np.zeros((0, ptR, burnin)),
+                theta_burnin=np.zeros((0, thR, burnin, d)), loglike_sampling=np.zeros((0, ptR, samples)),
+                logprior_sampling=np.zeros((0, ptR, samples)), theta_sampling=np.zeros((0, thR, samples, d)),
+                mc_accept_burnin=np.zeros((0, max(rungs - 1, 0)), np.int32), mc_accept_sampling=np.zeros((0, max(rungs - 1, 0)), np.int32),
+                accept_burnin=np.zeros((0, rungs), np.int32), accept_sampling=np.zeros((0, rungs), np.int32),
+                t_diff=np.zeros(0), bw_final=np.zeros((0, rungs, d)))
+
+
+def _thinned_frames(raw, names, burnin, samples, thin, chains, rungs, save_hot_draws):
+    """The `output` (cold rung) and `pt` (all stored rungs) data frames from draws thinned on the device: stored
+    iterations 0, thin, 2 thin, ... of each phase, numbered as the reference numbers them (1..burnin,
+    burnin+1..burnin+samples; R/main.R:420-482)."""
     th_b, th_s = raw["theta_burnin"][:, -1], raw["theta_sampling"][:, -1]  # [chains, kept, d]
     it_b = 1 + thin * np.arange(th_b.shape[1])
     it_s = burnin + 1 + thin * np.arange(th_s.shape[1])
     n_it = it_b.size + it_s.size
-    out = pd.DataFrame({"chain": np.repeat(np.arange(1, chains + 1), n_it),
-                        "phase": np.tile(np.concatenate([np.repeat("burnin", it_b.size), np.repeat("sampling", it_s.size)]), chains),
-                        "iteration": np.tile(np.concatenate([it_b, it_s]), chains)})
+    phase = np.concatenate([np.repeat("burnin", it_b.size), np.repeat("sampling", it_s.size)])
+    its = np.concatenate([it_b, it_s])
+    out = pd.DataFrame({"chain": np.repeat(np.arange(1, chains + 1), n_it), "phase": np.tile(phase, chains),
+                        "iteration": np.tile(its, chains)})
     theta = np.concatenate([th_b, th_s], axis=1).reshape(chains * n_it, len(names))
     for k, nm in enumerate(names):
         out[nm] = theta[:, k]
     out["logprior"] = np.concatenate([raw["logprior_burnin"][:, -1], raw["logprior_sampling"][:, -1]], axis=1).ravel()
     out["loglikelihood"] = np.concatenate([raw["loglike_burnin"][:, -1], raw["loglike_sampling"][:, -1]], axis=1).ravel()
-    return out
+    ptR = raw["loglike_burnin"].shape[1]
+    rung_ids = np.arange(1, rungs + 1) if ptR == rungs else np.array([rungs])
+    pt = pd.DataFrame({"chain": np.repeat(np.arange(1, chains + 1), ptR * n_it), "rung": np.tile(np.repeat(rung_ids, n_it), chains),
+                       "phase": np.tile(phase, chains * ptR), "iteration": np.tile(its, chains * ptR),
+                       "logprior": np.concatenate([raw["logprior_burnin"], raw["logprior_sampling"]], axis=2).ravel(),
+                       "loglikelihood": np.concatenate([raw["loglike_burnin"], raw["loglike_sampling"]], axis=2).ravel()})
+    if save_hot_draws and ptR == rungs:
+        th_all = np.concatenate([raw["theta_burnin"], raw["theta_sampling"]], axis=2).reshape(-1, len(names))
+        for k, nm in enumerate(names):
+            pt[nm] = th_all[:, k]
+    return out, pt
 
 
-def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, world, beta_raised, thin=None):
-    """output="summary": run the shard in a session, reduce the draws on the device, bring back only the
-    summaries and counters; across ranks the per-chain moments are gathered and the autocovariance sums
-    (about the global mean) added, plus the lag products that straddle two ranks' shards (from each shard's
-    first / last order.max draws), so the result equals the single-GPU one."""
-    sess = engine.Session(model, spec)
-    try:
-        nb = spec.burnin - 1
-        for phase, total in ((0, nb), (1, spec.samples)):
-            step = max(1, (total + 99) // 100) if progress is not None else max(total, 1)
-            done = 0
-            while done < total:
-                n = min(step, total - done)
-                sess.advance(n)
-                done += n
-                if progress is not None and progress(None, phase, done + (1 if phase == 0 else 0), spec.burnin if phase == 0 else spec.samples):
-                    raise DrjacobyError(15, "interrupted by the progress callback")
-        n_tot = chains * spec.samples
-        max_lag = min(n_tot - 1, int(np.floor(10 * np.log10(n_tot))))
-        first = sess.summary(max_lag=0, autocov=False)
-        mean, var = first["chain_mean"], first["chain_var"]
-        dev = np.array([first["deviance_mean_var"][0], first["deviance_mean_var"][1], spec.chains * spec.samples], dtype=np.float64)
-        if world > 1:
-            parts = gather_shards({"m": mean, "v": var, "dev": dev[None, :]}, chains, rank, world)
-            import torch
-            import torch.distributed as dist
-            backend = dist.get_backend()
-            devc = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-            ctr_t = torch.zeros(spec.d, dtype=torch.float64, device=devc)
+def _advance_with_progress(sess, spec, progress):
+    nb = spec.burnin - 1
+    for phase, total in ((0, nb), (1, spec.samples)):
+        step = max(1, (total + 99) // 100) if progress is not None else max(total, 1)
+        done = 0
+        while done < total:
+            n = min(step, total - done)
+            sess.advance(n)
+            done += n
+            if progress is not None and progress(None, phase, done + (1 if phase == 0 else 0), spec.burnin if phase == 0 else spec.samples):
+                raise DrjacobyError(15, "interrupted by the progress callback")
+
+
+def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, world, beta_raised, thin=None, devices=None,
+                 quantiles=None, shape=None):
+    """output="summary": run in a session, reduce the draws on the device(s), bring back only the summaries and counters.
+
+    One process (one GPU, or several through cluster="gpus"): ONE drj_session_summary / drj_multi_summary call -- the
+    merge over the devices (per-chain moments, autocovariance sums about the global mean plus the lag products that
+    straddle two devices' chain ranges, pooled deviance moments, radix-select histograms) happens inside the library.
+    cluster="torch": each rank reduces its shard; the moments are gathered, the autocovariance sums added over the
+    ranks plus the straddling lag products, so the result equals the single-GPU one.  A rank without chains (more
+    ranks than chains) skips the native calls and still enters every collective."""
+    burnin, samples, rungs, d, save_hot, store_pt = shape
+    n_tot = chains * samples
+    max_lag = min(n_tot - 1, int(np.floor(10 * np.log10(n_tot))))
+    quant = None
+    if world == 1:
+        sess = engine.Session(model, spec, devices=devices)
+        try:
+            _advance_with_progress(sess, spec, progress)
+            summ = sess.summary(max_lag=max_lag, quantiles=quantiles)
+            raw = sess.download(draws=False) if thin is None else sess.download(draws=True, thin=thin)
+        finally:
+            sess.close()
+        mean, var, ac = summ["chain_mean"], summ["chain_var"], summ["autocov_sum"]
+        dic = float(summ["deviance_mean_var"][0] + 0.5 * summ["deviance_mean_var"][1]) if n_tot > 1 else np.nan
+        quant = summ.get("quantiles")
+    else:
+        if quantiles is not None:
+            raise ValueError('quantiles= is not available with cluster="torch"; use cluster="gpus" (one process, several GPUs)')
+        import torch
+        import torch.distributed as dist
+        backend = dist.get_backend()
+        devc = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        sess = engine.Session(model, spec) if spec is not None else None
+        try:
+            if sess is not None:
+                _advance_with_progress(sess, spec, progress)
+                first = sess.summary(max_lag=0, autocov=False)
+                mean, var = first["chain_mean"], first["chain_var"]
+                dev = np.array([[first["deviance_mean_var"][0], first["deviance_mean_var"][1], spec.chains * spec.samples]], dtype=np.float64)
+            else:
+                mean, var, dev = np.zeros((0, d)), np.zeros((0, d)), np.zeros((0, 3))
+            parts = gather_shards({"m": mean, "v": var, "dev": dev}, chains, rank, world)
+            ctr_t = torch.zeros(d, dtype=torch.float64, device=devc)
             if rank == 0:
                 ctr_t += torch.from_numpy(parts["m"].mean(axis=0)).to(devc)
             dist.broadcast(ctr_t, src=0)
             center = ctr_t.cpu().numpy()
-        else:
-            parts = {"m": mean, "v": var, "dev": dev[None, :]}
-            center = mean.mean(axis=0)
-        second = sess.summary(max_lag=max_lag, center=center, moments=False)
-        ac = second["autocov_sum"]
-        if world > 1:
-            t = torch.from_numpy(ac).to(devc)
+            if sess is not None:
+                second = sess.summary(max_lag=max_lag, center=center, moments=False)
+                ac, hd, tl = second["autocov_sum"], second["head"][None], second["tail"][None]
+                raw = sess.download(draws=False) if thin is None else sess.download(draws=True, thin=thin)
+            else:
+                ac, hd, tl = np.zeros((d, max_lag + 1)), np.zeros((0, d, max(max_lag, 1))), np.zeros((0, d, max(max_lag, 1)))
+                raw = _empty_raw(-(-burnin // (thin or 1)), -(-samples // (thin or 1)), rungs, d, save_hot, store_pt)
+                if thin is None:
+                    raw = {k: v for k, v in raw.items() if k not in engine._DRAW_KEYS}
+            t = torch.from_numpy(np.ascontiguousarray(ac)).to(devc)
             dist.all_reduce(t)
             ac = t.cpu().numpy()
-        raw = sess.download(draws=False) if thin is None else sess.download(draws=True, thin=thin)
-        if world > 1:
             # one gather for the counters and for each shard's first / last max_lag draws
-            both = gather_shards(dict(raw, _head=second["head"][None], _tail=second["tail"][None]), chains, rank, world)
+            both = gather_shards(dict(raw, _head=hd, _tail=tl), chains, rank, world)
             if rank == 0:
                 hd_all, tl_all = both.pop("_head"), both.pop("_tail")
                 raw = both
-                # lag products that straddle two ranks' shards: tail of rank k x head of rank k+1
-                for k in range(world - 1):
+                # lag products that straddle two ranks' shards: tail of shard k x head of shard k+1 (shards with chains only)
+                for k in range(hd_all.shape[0] - 1):
                     if max_lag <= 0:
                         break
-                    tl, hd = tl_all[k] - center[:, None], hd_all[k + 1] - center[:, None]   # [d, L]
+                    tlk, hdk = tl_all[k] - center[:, None], hd_all[k + 1] - center[:, None]   # [d, L]
                     for lag in range(1, max_lag + 1):
                         # x_j in the last `lag` draws of shard k pairs with x_{j+lag} among the first `lag` of shard k+1
-                        ac[:, lag] += (tl[:, max_lag - lag:] * hd[:, :lag]).sum(axis=1)
+                        ac[:, lag] += (tlk[:, max_lag - lag:] * hdk[:, :lag]).sum(axis=1)
             else:
                 raw = None
-    finally:
-        sess.close()
-    if rank != 0:
-        return None, None
-    mean, var = parts["m"], parts["v"]
+        finally:
+            if sess is not None:
+                sess.close()
+        if rank != 0:
+            return None, None
+        mean, var = parts["m"], parts["v"]
+        # deviance over all ranks: pool the per-rank (mean, variance, count)
+        dv = parts["dev"]
+        n_all = dv[:, 2].sum()
+        gm = (dv[:, 0] * dv[:, 2]).sum() / n_all
+        m2 = (dv[:, 1] * (dv[:, 2] - 1) + dv[:, 2] * (dv[:, 0] - gm) ** 2).sum()
+        dic = float(gm + 0.5 * m2 / (n_all - 1)) if n_all > 1 else np.nan
     diagnostics = {"run_time": pd.DataFrame({"chain": np.arange(1, chains + 1), "seconds": raw["t_diff"]})}
-    if chains > 1 and spec.samples > 1:
-        diagnostics["rhat"] = pd.Series({nm: (np.nan if skip_param[k] else dg.gelman_rubin_from_moments(mean[:, k], var[:, k], spec.samples))
+    if chains > 1 and samples > 1:
+        diagnostics["rhat"] = pd.Series({nm: (np.nan if skip_param[k] else dg.gelman_rubin_from_moments(mean[:, k], var[:, k], samples))
                                          for k, nm in enumerate(names)})
     diagnostics["ess"] = pd.Series({nm: (np.nan if skip_param[k] else dg.ess_from_autocov(ac[k], n_tot)) for k, nm in enumerate(names)})
-    diagnostics["rung_details"] = pd.DataFrame({"rung": np.arange(1, spec.rungs + 1), "thermodynamic_power": beta_raised})
-    if spec.rungs > 1:
-        link = np.tile(np.arange(1, spec.rungs), chains)
-        chain = np.repeat(np.arange(1, chains + 1), spec.rungs - 1)
+    diagnostics["rung_details"] = pd.DataFrame({"rung": np.arange(1, rungs + 1), "thermodynamic_power": beta_raised})
+    if rungs > 1:
+        link = np.tile(np.arange(1, rungs), chains)
+        chain = np.repeat(np.arange(1, chains + 1), rungs - 1)
         diagnostics["mc_accept"] = pd.concat([
-            pd.DataFrame({"link": link, "chain": chain, "phase": "burnin", "value": raw["mc_accept_burnin"].ravel() / spec.burnin}),
-            pd.DataFrame({"link": link, "chain": chain, "phase": "sampling", "value": raw["mc_accept_sampling"].ravel() / spec.samples})],
+            pd.DataFrame({"link": link, "chain": chain, "phase": "burnin", "value": raw["mc_accept_burnin"].ravel() / burnin}),
+            pd.DataFrame({"link": link, "chain": chain, "phase": "sampling", "value": raw["mc_accept_sampling"].ravel() / samples})],
             ignore_index=True)
     else:
         diagnostics["mc_accept"] = np.nan
-    # deviance over all ranks: pool the per-rank (mean, variance, count)
-    d = parts["dev"]
-    n_all = d[:, 2].sum()
-    gm = (d[:, 0] * d[:, 2]).sum() / n_all
-    m2 = (d[:, 1] * (d[:, 2] - 1) + d[:, 2] * (d[:, 0] - gm) ** 2).sum()
-    diagnostics["DIC_Gelman"] = float(gm + 0.5 * m2 / (n_all - 1)) if n_all > 1 else np.nan
+    diagnostics["DIC_Gelman"] = dic
     diagnostics["posterior_mean"] = pd.Series({nm: float(mean[:, k].mean()) for k, nm in enumerate(names)})
+    if quant is not None:
+        probs = np.ascontiguousarray(quantiles, dtype=np.float64).ravel()
+        diagnostics["quantiles"] = pd.DataFrame(quant.T, index=[f"{100 * p:g}%" for p in probs], columns=names)
     raw = dict(raw, chain_mean=mean, chain_var=var, autocov_sum=ac)
     return raw, diagnostics
 
@@ -520,14 +604,6 @@ def _run_summary(model, spec, progress, *, names, skip_param, chains, rank, worl
 def _printed_rate(acc, n, d):
     v = float(acc) / float(n * d) * 1000.0
     return np.floor(abs(v) + 0.5) / 10.0
-
-
-# indirection so that the multi-rank plumbing can be exercised on CPU (gloo) with a stub engine
-_SHARD_RUNNER = engine.run_raw
-
-
-def _run_shard(model, spec, progress):
-    return _SHARD_RUNNER(model, spec, progress)
 
 
 def shard_range(chains: int, rank: int, world: int) -> tuple[int, int]:

@@ -107,7 +107,7 @@ __device__ __forceinline__ double drj_rnorm(double mu, double sigma, double u1, 
   if (sigma == 0.0 || !isfinite(mu)) return mu;
   const double BIG = 134217728.0;  // 2^27
   double u = (double)(int)(BIG * u1) + u2;
-  return mu + sigma * drj_qnorm(u / BIG);
+  return __dadd_rn(mu, __dmul_rn(sigma, drj_qnorm(u / BIG)));  // mu + sigma * norm_rand(), product rounded as in R
 }
 
 // ----------------------------------------------------------------------------- nmath

@@ -25,6 +25,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/drjacoby_b200.h"
@@ -259,6 +260,48 @@ __global__ void drj_series_ends(const double* __restrict__ src, long long cs, lo
   }
 }
 
+// ---- quantiles by radix select (R/main.R's consumers call quantile() on mcmc$output; at GPU chain counts the
+// draws cannot leave the device).  One pass = one 11-bit digit of the order-preserving 64-bit key of a double:
+// every draw of parameter blockIdx.y whose high `bits_done` bits equal the prefix of one of the parameter's groups
+// is counted in that group's 2048-bin histogram (shared memory, warp-aggregated: the first digits -- sign and
+// exponent -- put nearly all draws of a parameter in two or three bins), then the non-empty bins are added to
+// the global histogram.  The host picks the bin holding each wanted rank and descends (6 passes: 11,11,11,11,11,9 bits).
+#define DRJ_QBINS 2048
+__device__ __forceinline__ unsigned long long drj_order_key(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__global__ void __launch_bounds__(256) drj_quantile_hist(const double* __restrict__ src, long long cs, long long ts, int S, int C,
+                                                        int bits_done, int nbits, const unsigned long long* __restrict__ prefix,
+                                                        const int* __restrict__ group_ptr /*[D+1]*/, unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int qh[];  // [groups of this parameter][DRJ_QBINS]
+  const int k = blockIdx.y;
+  const int g0 = group_ptr[k], ng = group_ptr[k + 1] - g0;
+  if (ng == 0) return;
+  for (int i = threadIdx.x; i < ng * DRJ_QBINS; i += blockDim.x) qh[i] = 0u;
+  __syncthreads();
+  const int shift = 64 - bits_done - nbits;
+  const unsigned mask = (1u << nbits) - 1u;
+  const int lane = threadIdx.x & 31;
+  for (int c = blockIdx.x; c < C; c += gridDim.x) {
+    const double* x = src + (long long)c * cs + k;
+    for (int t0 = 0; t0 < S; t0 += blockDim.x) {
+      const int t = t0 + threadIdx.x;
+      const bool in = t < S;
+      const unsigned long long key = in ? drj_order_key(x[(long long)t * ts]) : 0ULL;
+      const unsigned bin = (unsigned)(key >> shift) & mask;
+      for (int g = 0; g < ng; ++g) {
+        const bool hit = in && (bits_done == 0 || (key >> (64 - bits_done)) == prefix[g0 + g]);
+        const unsigned peers = __match_any_sync(0xffffffffu, hit ? bin : 0xffffffffu);
+        if (hit && lane == __ffs(peers) - 1) atomicAdd(&qh[g * DRJ_QBINS + bin], (unsigned)__popc(peers));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ng * DRJ_QBINS; i += blockDim.x)
+    if (qh[i]) atomicAdd(&hist[(long long)g0 * DRJ_QBINS + i], (unsigned long long)qh[i]);
+}
+
 // FP64 FMA throughput probe: 8 independent dependent-chains per thread
 __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
@@ -276,6 +319,13 @@ __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, do
 // ------------------------------------------------------------------------------------------------
 // models: built-in registry + NVRTC
 // ------------------------------------------------------------------------------------------------
+// a source model's kernels on ONE device (a CUmodule belongs to a context)
+struct JitFuncs {
+  CUmodule module = nullptr;
+  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr,
+             init_chain_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr;
+};
+
 struct drj_model {
   std::string name;
   int D = 0, NBLOCK = 0;
@@ -287,9 +337,13 @@ struct drj_model {
   const void* stream_fn = nullptr; // sweep variant for data streamed through shared memory (datum-form models)
   const void* team_init_fn = nullptr;   // cluster-per-chain variants (datum-form models)
   const void* team_sweep_fn = nullptr;
-  CUmodule module = nullptr;       // jit
-  CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr,
-             init_chain_cu = nullptr;
+  const void* grid_init_fn = nullptr;   // grid-per-run variants (datum-form models)
+  const void* grid_sweep_fn = nullptr;
+  // jit: the compiled cubin, loaded into a device's context on first use there (a model serves every device:
+  // drj_run_mcmc_multi drives all GPUs from one model handle)
+  std::vector<char> cubin;
+  mutable std::map<int, JitFuncs> per_device;
+  mutable std::mutex mu;
   double compile_seconds = 0.0;
   int device = 0;
 };
@@ -304,6 +358,8 @@ struct BuiltinEntry {
   const void* team_init_fn;
   const void* team_sweep_fn;
   const void* init_chain_fn;
+  const void* grid_init_fn;
+  const void* grid_sweep_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
@@ -311,7 +367,8 @@ struct BuiltinEntry {
     NAME, __VA_ARGS__::D, __VA_ARGS__::NBLOCK, __VA_ARGS__::DATUM_FORM,                  \
         (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__, false>, \
         DrjStreamKernel<__VA_ARGS__>::get(), DrjStreamKernel<__VA_ARGS__>::team_init(),                \
-        DrjStreamKernel<__VA_ARGS__>::team_sweep(), (const void*)drj_init_chain_kernel<__VA_ARGS__>    \
+        DrjStreamKernel<__VA_ARGS__>::team_sweep(), (const void*)drj_init_chain_kernel<__VA_ARGS__>,   \
+        DrjStreamKernel<__VA_ARGS__>::grid_init(), DrjStreamKernel<__VA_ARGS__>::grid_sweep()          \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -343,6 +400,9 @@ struct DriverApi {
                            CUstream, void**, void**) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;
+  CUresult (*LaunchCooperativeKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                      CUstream, void**) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
   CUresult (*OccupancyMaxActiveClusters)(int*, CUfunction, const CUlaunchConfig*) = nullptr;
   bool ok = false;
@@ -359,6 +419,8 @@ static bool load_driver_api() {
       {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
       {"cuGetErrorString", (void**)&g_drv.GetErrorString},
       {"cuLaunchKernelEx", (void**)&g_drv.LaunchKernelEx},
+      {"cuLaunchCooperativeKernel", (void**)&g_drv.LaunchCooperativeKernel},
+      {"cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&g_drv.OccupancyMaxActiveBlocksPerMultiprocessor},
       {"cuFuncSetAttribute", (void**)&g_drv.FuncSetAttribute},
       {"cuOccupancyMaxActiveClusters", (void**)&g_drv.OccupancyMaxActiveClusters},
   };
@@ -435,11 +497,38 @@ static bool valid_ident(const char* s) {
   return true;
 }
 
+// The cubin cache directory, or "" when no safe one is available (then every source model is compiled afresh).
+// $DRJ_CACHE_DIR, else $XDG_CACHE_HOME/drjacoby_b200, else ~/.cache/drjacoby_b200, else /tmp/drjacoby_b200_cache_<uid>.
+// The directory must be a real directory (not a symlink) owned by this user and closed to everybody else:
+// a cached cubin is code that will run in this process, so a directory another local user could have
+// created or can write to is never used.
 static std::string cache_dir() {
-  const char* e = getenv("DRJ_CACHE_DIR");
-  std::string d = e ? e : (std::string("/tmp/drjacoby_b200_cache_") + std::to_string((long)getuid()));
-  mkdir(d.c_str(), 0700);
-  return d;
+  std::string d;
+  if (const char* e = getenv("DRJ_CACHE_DIR")) d = e;
+  else if (const char* x = getenv("XDG_CACHE_HOME")) { if (*x) { mkdir(x, 0700); d = std::string(x) + "/drjacoby_b200"; } }
+  if (d.empty()) {
+    if (const char* h = getenv("HOME")) {
+      if (*h) { const std::string c = std::string(h) + "/.cache"; mkdir(c.c_str(), 0700); d = c + "/drjacoby_b200"; }
+    }
+  }
+  if (d.empty()) d = std::string("/tmp/drjacoby_b200_cache_") + std::to_string((long)getuid());
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    mkdir(d.c_str(), 0700);
+    struct stat st;
+    if (lstat(d.c_str(), &st) == 0 && S_ISDIR(st.st_mode) && st.st_uid == getuid() && (st.st_mode & 077) == 0) return d;
+    if (attempt == 0 && !getenv("DRJ_CACHE_DIR")) d = std::string("/tmp/drjacoby_b200_cache_") + std::to_string((long)getuid());
+    else break;
+  }
+  return std::string();
+}
+
+// second, independent 64-bit hash (different offset basis and a final avalanche): the cache file carries both
+// hashes and the length of the key text, and an entry is used only if all three match
+static uint64_t fnv1a_alt(const std::string& s) {
+  uint64_t h = 0x9ae16a3b2f90404fULL;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ULL; h ^= h >> 29; }
+  h ^= h >> 32; h *= 0xd6e8feb86659fd93ULL; h ^= h >> 32;
+  return h;
 }
 
 // Generates the translation unit for a source model: index constants from the name arrays, the
@@ -479,45 +568,85 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "static_assert(DRJ_USER_MODEL::D == DRJ_D, \"model D does not match df_params\");\n"
        "static_assert(DRJ_USER_MODEL::NBLOCK == DRJ_NBLOCK, \"model NBLOCK does not match df_params$block\");\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  drj_init_body<DRJ_USER_MODEL, false>(a);\n"
+       "  drj_init_body<DRJ_USER_MODEL, DRJ_MODE_SOLO>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT) drj_user_init_chain(const __grid_constant__ DrjKernelArgs a) {\n"
        "  drj_init_chain_body<DRJ_USER_MODEL>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  drj_sweep_body<DRJ_USER_MODEL, false, false>(a);\n"
+       "  drj_sweep_body<DRJ_USER_MODEL, false, DRJ_MODE_SOLO>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_stream(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true, false>(a);\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true, DRJ_MODE_SOLO>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_user_init_team(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_init_body<DRJ_USER_MODEL, true>(a);\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_init_body<DRJ_USER_MODEL, DRJ_MODE_TEAM>(a);\n"
        "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_user_sweep_team(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, false, true>(a);\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, false, DRJ_MODE_TEAM>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_init_grid(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_init_body<DRJ_USER_MODEL, DRJ_MODE_GRID>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_sweep_grid(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, false, DRJ_MODE_GRID>(a);\n"
        "}\n"
        "extern \"C\" __global__ void drj_user_traits(int* out) { out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0; }\n";
   return s;
 }
 
+// load the model's cubin into the current device's context (once per device) and look its kernels up
+static int jit_functions(const drj_model* m, int device, const JitFuncs** out, drj_error* err) {
+  std::lock_guard<std::mutex> lock(m->mu);
+  auto it = m->per_device.find(device);
+  if (it != m->per_device.end()) { *out = &it->second; return DRJ_OK; }
+  if (!load_driver_api()) return set_err(err, DRJ_ERR_CUDA, "CUDA driver entry points unavailable");
+  JitFuncs f;
+  CUresult cr = g_drv.ModuleLoadData(&f.module, m->cubin.data());
+  if (cr != CUDA_SUCCESS) {
+    const char* es = nullptr;
+    g_drv.GetErrorString(cr, &es);
+    return set_err(err, DRJ_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
+  }
+  if (g_drv.ModuleGetFunction(&f.init_cu, f.module, "drj_user_init") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.sweep_cu, f.module, "drj_user_sweep") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.stream_cu, f.module, "drj_user_sweep_stream") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.team_init_cu, f.module, "drj_user_init_team") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.team_sweep_cu, f.module, "drj_user_sweep_team") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.grid_init_cu, f.module, "drj_user_init_grid") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.grid_sweep_cu, f.module, "drj_user_sweep_grid") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.init_chain_cu, f.module, "drj_user_init_chain") != CUDA_SUCCESS) {
+    g_drv.ModuleUnload(f.module);
+    return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
+  }
+  *out = &(m->per_device[device] = f);
+  return DRJ_OK;
+}
+
 static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
   const double t0 = wall_now();
   const std::string src = make_jit_source(desc);
-  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v5";
-  char hex[32];
-  snprintf(hex, sizeof(hex), "%016llx", (unsigned long long)fnv1a(key_text));
-  const std::string path = cache_dir() + "/" + hex + ".cubin";
-  std::vector<char> cubin;
-  if (FILE* f = fopen(path.c_str(), "rb")) {
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (n > 0) {
-      cubin.resize(n);
-      if (fread(cubin.data(), 1, n, f) != (size_t)n) cubin.clear();
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v6";
+  const uint64_t h1 = fnv1a(key_text), h2 = fnv1a_alt(key_text), klen = (uint64_t)key_text.size();
+  char hex[40];
+  snprintf(hex, sizeof(hex), "%016llx%08llx", (unsigned long long)h1, (unsigned long long)(h2 & 0xffffffffULL));
+  const std::string dir = cache_dir();
+  const std::string path = dir.empty() ? std::string() : dir + "/" + hex + ".cubin";
+  std::vector<char>& cubin = m->cubin;
+  cubin.clear();
+  // cache file = { magic, h1, h2, key length } + cubin; anything that does not match is ignored and rewritten
+  const uint64_t magic = 0x324e494255434a44ULL;  // "DJCUBIN2"
+  if (!path.empty())
+    if (FILE* f = fopen(path.c_str(), "rb")) {
+      uint64_t hdr[4] = {0, 0, 0, 0};
+      struct stat st;
+      if (fstat(fileno(f), &st) == 0 && st.st_uid == getuid() && (st.st_mode & 022) == 0 && st.st_size > (off_t)sizeof(hdr) &&
+          fread(hdr, sizeof(hdr), 1, f) == 1 && hdr[0] == magic && hdr[1] == h1 && hdr[2] == h2 && hdr[3] == klen) {
+        cubin.resize((size_t)st.st_size - sizeof(hdr));
+        if (fread(cubin.data(), 1, cubin.size(), f) != cubin.size()) cubin.clear();
+      }
+      fclose(f);
     }
-    fclose(f);
-  }
   if (cubin.empty()) {
     std::string why;
     if (!load_nvrtc(why)) return set_err(err, DRJ_ERR_COMPILE, "NVRTC unavailable: %s", why.c_str());
@@ -542,32 +671,25 @@ static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err)
     g_nvrtc.GetCUBIN(prog, cubin.data());
     g_nvrtc.DestroyProgram(&prog);
     m->compile_seconds = wall_now() - t0;
-    const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
-    if (FILE* f = fopen(tmp.c_str(), "wb")) {
-      fwrite(cubin.data(), 1, cubin.size(), f);
-      fclose(f);
-      rename(tmp.c_str(), path.c_str());
+    if (!path.empty()) {
+      const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+      if (FILE* f = fopen(tmp.c_str(), "wb")) {
+        const uint64_t hdr[4] = {magic, h1, h2, klen};
+        const bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+        fclose(f);
+        if (ok) { chmod(tmp.c_str(), 0600); rename(tmp.c_str(), path.c_str()); }
+        else unlink(tmp.c_str());
+      }
     }
   }
-  if (!load_driver_api()) return set_err(err, DRJ_ERR_CUDA, "CUDA driver entry points unavailable");
-  CUresult cr = g_drv.ModuleLoadData(&m->module, cubin.data());
-  if (cr != CUDA_SUCCESS) {
-    const char* es = nullptr;
-    g_drv.GetErrorString(cr, &es);
-    return set_err(err, DRJ_ERR_CUDA, "cuModuleLoadData: %s", es ? es : "?");
-  }
-  if (g_drv.ModuleGetFunction(&m->init_cu, m->module, "drj_user_init") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->sweep_cu, m->module, "drj_user_sweep") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->stream_cu, m->module, "drj_user_sweep_stream") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->team_init_cu, m->module, "drj_user_init_team") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->team_sweep_cu, m->module, "drj_user_sweep_team") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&m->init_chain_cu, m->module, "drj_user_init_chain") != CUDA_SUCCESS)
-    return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
+  const JitFuncs* jf = nullptr;
+  int rc = jit_functions(m, m->device, &jf, err);
+  if (rc) return rc;
   {  // does the user's model use the per-datum form?
     CUfunction traits = nullptr;
     int* d_flag = nullptr;
     int h_flag = 0;
-    if (g_drv.ModuleGetFunction(&traits, m->module, "drj_user_traits") == CUDA_SUCCESS &&
+    if (g_drv.ModuleGetFunction(&traits, jf->module, "drj_user_traits") == CUDA_SUCCESS &&
         cudaMalloc(&d_flag, sizeof(int)) == cudaSuccess) {
       void* params[] = {(void*)&d_flag};
       if (g_drv.LaunchKernel(traits, 1, 1, 1, 1, 1, 1, 0, nullptr, params, nullptr) == CUDA_SUCCESS &&
@@ -602,6 +724,7 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       m->name = b.name; m->D = b.D; m->NBLOCK = b.NBLOCK; m->datum_form = b.datum_form;
       m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->stream_fn = b.stream_fn; m->device = device;
       m->team_init_fn = b.team_init_fn; m->team_sweep_fn = b.team_sweep_fn; m->init_chain_fn = b.init_chain_fn;
+      m->grid_init_fn = b.grid_init_fn; m->grid_sweep_fn = b.grid_sweep_fn;
       *out = m;
       return DRJ_OK;
     }
@@ -623,6 +746,9 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
   }
   if (!desc->cuda_source) return set_err(err, DRJ_ERR_MODEL, "model has neither a built-in name nor CUDA source");
   if (desc->d < 1 || desc->n_block < 1) return set_err(err, DRJ_ERR_ARG, "source model needs d >= 1 and n_block >= 1");
+  // the two names are spliced into the generated translation unit: identifiers only
+  if ((desc->loglike_name && !valid_ident(desc->loglike_name)) || (desc->logprior_name && !valid_ident(desc->logprior_name)))
+    return set_err(err, DRJ_ERR_ARG, "loglike / logprior must be plain C identifiers (the names of __device__ functions)");
   if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return set_err(err, DRJ_ERR_CUDA, "no CUDA device %d", device); }
   cudaFree(0);  // make sure the primary context exists before the driver API is used
   std::lock_guard<std::mutex> lock(g_mutex);
@@ -636,7 +762,13 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
 
 extern "C" void drj_model_destroy(drj_model* m) {
   if (!m) return;
-  if (m->module && g_drv.ok) g_drv.ModuleUnload(m->module);
+  if (g_drv.ok) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : m->per_device)
+      if (kv.second.module && cudaSetDevice(kv.first) == cudaSuccess) g_drv.ModuleUnload(kv.second.module);
+    cudaSetDevice(cur);
+  }
   delete m;
 }
 
@@ -748,13 +880,16 @@ struct drj_session {
   bool team = false;            // few chains x long data: cluster-per-chain kernels (drj_sweep_item_team)
   int team_ctas = 1;            // CTAs per cluster
   bool team_ctas_forced = false;
+  bool gridk = false;           // few particles x data >> L2: grid-per-run kernels (drj_sweep_item_grid), cooperative launch
+  unsigned int* grid_bar = nullptr;
+  const JitFuncs* jf = nullptr; // source model: its kernels in this device's context
   unsigned dyn_smem = 0;        // dynamic shared memory of the model kernels: the data tile buffer
   double t_create = 0.0;
   bool failed = false;
   // summary scratch, kept for the life of the session (grow-only): cudaMalloc / cudaFree on every
   // drj_session_summary call cost up to ~0.5 s now and then next to tens of GB of stored draws
-  void* scratch[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  void* scratch[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static cudaError_t scratch_get(drj_session* s, int slot, size_t bytes, double** out) {
@@ -823,19 +958,21 @@ static cudaError_t upload_list(drj_session* s, const drj_list* l, DrjList* out) 
   return e;
 }
 
-// initial likelihood and prior, one thread per chain (not for the cluster kernels, whose init kernel does it itself)
+static int cu_fail(drj_error* err, const char* what, CUresult cr) {
+  const char* es = nullptr;
+  g_drv.GetErrorString(cr, &es);
+  return set_err(err, DRJ_ERR_CUDA, "%s: %s", what, es ? es : "?");
+}
+
+// initial likelihood and prior, one thread per chain (not for the cluster / grid kernels, whose init kernel does it itself)
 static int launch_init_chain(drj_session* s, drj_error* err) {
   const drj_model* m = s->model;
   void* params[] = {(void*)&s->a};
   const unsigned threads = (unsigned)std::min(128, ((s->C + 31) / 32) * 32);
   const unsigned grid = (unsigned)((s->C + threads - 1) / threads);
   if (m->jit) {
-    CUresult cr = g_drv.LaunchKernel(m->init_chain_cu, grid, 1, 1, threads, 1, 1, s->dyn_smem, (CUstream)s->stream, params, nullptr);
-    if (cr != CUDA_SUCCESS) {
-      const char* es = nullptr;
-      g_drv.GetErrorString(cr, &es);
-      return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernel: %s", es ? es : "?");
-    }
+    CUresult cr = g_drv.LaunchKernel(s->jf->init_chain_cu, grid, 1, 1, threads, 1, 1, s->dyn_smem, (CUstream)s->stream, params, nullptr);
+    if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
   } else {
     CUDA_TRY(cudaLaunchKernel(m->init_chain_fn, dim3(grid), dim3(threads), params, s->dyn_smem, s->stream));
   }
@@ -847,6 +984,18 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
   const drj_model* m = s->model;
   void* params[] = {(void*)&s->a};
   const bool stream = sweep && s->stream_variant;
+  if (s->gridk) {  // the whole grid is one team: cooperative launch (all CTAs co-resident), barrier counter at 0
+    CUDA_TRY(cudaMemsetAsync(s->grid_bar, 0, sizeof(unsigned int), s->stream));
+    if (m->jit) {
+      CUresult cr = g_drv.LaunchCooperativeKernel(sweep ? s->jf->grid_sweep_cu : s->jf->grid_init_cu, (unsigned)s->grid, 1, 1,
+                                                  (unsigned)s->nthreads, 1, 1, s->dyn_smem, (CUstream)s->stream, params);
+      if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchCooperativeKernel", cr);
+    } else {
+      CUDA_TRY(cudaLaunchCooperativeKernel(sweep ? m->grid_sweep_fn : m->grid_init_fn, dim3(s->grid), dim3(s->nthreads), params,
+                                           s->dyn_smem, s->stream));
+    }
+    return DRJ_OK;
+  }
   if (s->team) {  // one cluster of team_ctas CTAs per chain
     if (m->jit) {
       CUlaunchAttribute at[1];
@@ -857,12 +1006,8 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
       lc.gridDimX = (unsigned)s->grid; lc.gridDimY = 1; lc.gridDimZ = 1;
       lc.blockDimX = (unsigned)s->nthreads; lc.blockDimY = 1; lc.blockDimZ = 1;
       lc.sharedMemBytes = s->dyn_smem; lc.hStream = (CUstream)s->stream; lc.attrs = at; lc.numAttrs = 1;
-      CUresult cr = g_drv.LaunchKernelEx(&lc, sweep ? m->team_sweep_cu : m->team_init_cu, params, nullptr);
-      if (cr != CUDA_SUCCESS) {
-        const char* es = nullptr;
-        g_drv.GetErrorString(cr, &es);
-        return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernelEx: %s", es ? es : "?");
-      }
+      CUresult cr = g_drv.LaunchKernelEx(&lc, sweep ? s->jf->team_sweep_cu : s->jf->team_init_cu, params, nullptr);
+      if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernelEx", cr);
     } else {
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -876,13 +1021,9 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
     return DRJ_OK;
   }
   if (m->jit) {
-    CUresult cr = g_drv.LaunchKernel(!sweep ? m->init_cu : (stream ? m->stream_cu : m->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1, s->dyn_smem,
-                                     (CUstream)s->stream, params, nullptr);
-    if (cr != CUDA_SUCCESS) {
-      const char* es = nullptr;
-      g_drv.GetErrorString(cr, &es);
-      return set_err(err, DRJ_ERR_CUDA, "cuLaunchKernel: %s", es ? es : "?");
-    }
+    CUresult cr = g_drv.LaunchKernel(!sweep ? s->jf->init_cu : (stream ? s->jf->stream_cu : s->jf->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1,
+                                     s->dyn_smem, (CUstream)s->stream, params, nullptr);
+    if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
   } else {
     CUDA_TRY(cudaLaunchKernel(!sweep ? m->init_fn : (stream ? m->stream_fn : m->sweep_fn), dim3(s->grid), dim3(s->nthreads),
                               params, s->dyn_smem, s->stream));
@@ -896,13 +1037,60 @@ static int prop_sms(const drj_session* s) {
   return n;
 }
 
+// the one-thread-per-particle kernels: opt in to more than 48 KB of dynamic shared memory when the tile buffer
+// plus the per-parameter tables need it (a per-datum model with many parameters)
+static int solo_configure(drj_session* s, drj_error* err) {
+  if ((size_t)s->dyn_smem + 24u * (size_t)s->D + 16384u <= 48u * 1024u) return DRJ_OK;  // static + dynamic within the default limit
+  const drj_model* m = s->model;
+  if (m->jit) {
+    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->stream_cu})
+      if (f && g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
+        return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed (dynamic shared memory %u bytes)", s->dyn_smem);
+  } else {
+    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->stream_fn})
+      if (f) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
+  }
+  return DRJ_OK;
+}
+
+// GRID kernels: opt in to the dynamic shared memory of the chunk pipeline; grid = every CTA the device can hold at once
+static int grid_configure(drj_session* s, drj_error* err) {
+  const drj_model* m = s->model;
+  int per_sm = 0;
+  if (m->jit) {
+    for (CUfunction f : {s->jf->grid_init_cu, s->jf->grid_sweep_cu})
+      if (g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
+        return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed for the grid kernels");
+    int a = 0, b = 0;
+    if (g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&a, s->jf->grid_sweep_cu, s->nthreads, s->dyn_smem) != CUDA_SUCCESS ||
+        g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&b, s->jf->grid_init_cu, s->nthreads, s->dyn_smem) != CUDA_SUCCESS)
+      return set_err(err, DRJ_ERR_CUDA, "cuOccupancyMaxActiveBlocksPerMultiprocessor failed for the grid kernels");
+    per_sm = std::min(a, b);
+  } else {
+    for (const void* f : {m->grid_init_fn, m->grid_sweep_fn})
+      CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
+    int a = 0, b = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, m->grid_sweep_fn, s->nthreads, s->dyn_smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, m->grid_init_fn, s->nthreads, s->dyn_smem));
+    per_sm = std::min(a, b);
+  }
+  if (per_sm < 1) return set_err(err, DRJ_ERR_CUDA, "the grid kernels do not fit on an SM (%u bytes of shared memory)", s->dyn_smem);
+  int ctas = prop_sms(s);  // one CTA per SM streams 1/n_SM of the item
+  if (const char* e = getenv("DRJ_GRID_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1) ctas = std::min(v, prop_sms(s) * per_sm);
+  }
+  s->grid = ctas;
+  return DRJ_OK;
+}
+
 // TEAM kernels: opt in to the dynamic shared memory of the tile pipeline and to clusters of 16 CTAs, then
 // shrink the cluster until the device can co-schedule at least one
 static int team_configure(drj_session* s, drj_error* err) {
   const drj_model* m = s->model;
   for (int which = 0; which < 2; ++which) {
     if (m->jit) {
-      CUfunction f = which ? m->team_sweep_cu : m->team_init_cu;
+      CUfunction f = which ? s->jf->team_sweep_cu : s->jf->team_init_cu;
       CUresult cr = g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem);
       if (cr == CUDA_SUCCESS) cr = g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_NON_PORTABLE_CLUSTER_SIZE_ALLOWED, 1);
       if (cr != CUDA_SUCCESS) return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed for the cluster kernels");
@@ -923,7 +1111,7 @@ static int team_configure(drj_session* s, drj_error* err) {
       lc.gridDimX = (unsigned)s->team_ctas; lc.gridDimY = 1; lc.gridDimZ = 1;
       lc.blockDimX = (unsigned)s->nthreads; lc.blockDimY = 1; lc.blockDimZ = 1;
       lc.sharedMemBytes = s->dyn_smem; lc.attrs = at; lc.numAttrs = 1;
-      if (g_drv.OccupancyMaxActiveClusters(&nclusters, m->team_sweep_cu, &lc) != CUDA_SUCCESS) nclusters = 0;
+      if (g_drv.OccupancyMaxActiveClusters(&nclusters, s->jf->team_sweep_cu, &lc) != CUDA_SUCCESS) nclusters = 0;
     } else {
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1017,6 +1205,8 @@ static int validate(const drj_config* c, const drj_model* m, const drj_list* dat
     return set_err(err, DRJ_ERR_MODEL, "model '%s' has d=%d, n_block=%d but the config has d=%d, n_block=%d", m->name.c_str(),
                    m->D, m->NBLOCK, c->d, c->n_block);
   if (c->rungs > DRJ_NT) return set_err(err, DRJ_ERR_ARG, "rungs > %d not supported", DRJ_NT);
+  if (m->datum_form && c->d > 256) return set_err(err, DRJ_ERR_ARG, "per-datum (DATUM_FORM) models support at most 256 parameters; use the generic form");
+  if (c->layout_chains < 0) return set_err(err, DRJ_ERR_ARG, "layout_chains must be >= 0");
   if (c->d > 1022) return set_err(err, DRJ_ERR_ARG, "d > 1022 not supported");
   if (c->chains >= (1 << 24)) return set_err(err, DRJ_ERR_ARG, "more than 2^24-1 chains per call: shard the run");
   if (!(c->target_acceptance >= 0.0 && c->target_acceptance <= 1.0)) return set_err(err, DRJ_ERR_ARG, "target_acceptance must be in [0,1]");
@@ -1067,7 +1257,11 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   CUDA_TRY(cudaEventCreate(&s->ev0));
   CUDA_TRY(cudaEventCreate(&s->ev1));
   CUDA_TRY(cudaEventCreate(&s->ev2));
-  if (model->jit && !load_driver_api()) return set_err(err, DRJ_ERR_CUDA, "CUDA driver entry points unavailable");
+  if (model->jit) {
+    cudaFree(0);  // the primary context of this device must exist before the driver API is used
+    int rc = jit_functions(model, cfg->device, &s->jf, err);
+    if (rc) return rc;
+  }
 
   // ---- launch geometry: all rungs of a chain in one CTA, as many chains per CTA as fit in DRJ_NT
   // threads, but no more than needed to give every SM a few CTAs
@@ -1106,6 +1300,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   int tb = cfg->iters_per_launch > 0 ? cfg->iters_per_launch : (int)std::min(1024.0, std::max(1.0, 268435456.0 / ring_row));
   tb = std::max(1, std::min(tb, std::max(1, s->T_total)));
   tb = std::min(tb, (1 << 20) - 1);
+  tb = std::min(tb, std::max(1, 4000000 / (D * B + 1)));  // (grid kernels: the barrier counter of a launch stays below 2^32)
   s->tb = tb;
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
@@ -1120,10 +1315,10 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   // datum-form model with a long data item -> the sweep-kernel variant that parks the particle state in
   // HBM across data sweeps (mandatory when the item is streamed, n > 2 tiles; measured faster from
   // n ~ 2048 on even when the data is resident in shared memory: tools/n_sweep.py)
-  if (model->datum_form && data && (model->jit ? model->stream_cu != nullptr : model->stream_fn != nullptr))
+  if (model->datum_form && data && (model->jit ? s->jf->stream_cu != nullptr : model->stream_fn != nullptr))
     for (int k = 0; k < data->n_items; ++k)
       if (data->lengths[k] >= DRJ_TILE) s->stream_variant = true;
-  if (model->datum_form && (model->jit ? model->stream_cu != nullptr : model->stream_fn != nullptr)) {
+  if (model->datum_form && (model->jit ? s->jf->stream_cu != nullptr : model->stream_fn != nullptr)) {
     if (cfg->flags & DRJ_FLAG_STREAM_KERNEL) s->stream_variant = true;    // tuning / testing overrides
     if (cfg->flags & DRJ_FLAG_RESIDENT_KERNEL) s->stream_variant = false;
   }
@@ -1131,13 +1326,40 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   // few chains over a long data item -> one thread-block cluster per chain, the sweep divided over the
   // cluster's threads (drj_sweep_item_team).  With P = chains x rungs threads the one-thread-per-particle
   // kernels need ~5 cycles per datum per sweep whatever P is, until P fills the machine (~75k threads).
+  // The family is chosen from the WHOLE run's particle count when this call is a shard of a larger run
+  // (cfg->layout_chains): the families associate the likelihood sum differently, so every shard must use the one
+  // the unsharded run would use to stay bit-identical with it.
+  const long long layout_C = cfg->layout_chains > 0 ? std::max(cfg->layout_chains, C) : C;
+  const long long layout_P = layout_C * R;
   int team_stages = 3;  // x 64 KB tiles
+  int grid_stages = 6;  // x 16 KB chunks
   {
     long long longest = 0;
     if (data) for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
-    const bool can = model->datum_form && data && R <= DRJ_TEAM_MAXR &&
-                     (model->jit ? (model->team_sweep_cu != nullptr && g_drv.LaunchKernelEx != nullptr) : model->team_sweep_fn != nullptr);
-    bool want = longest > 2LL * DRJ_TILE && P <= 4096;  // measured cross-over, tools/team_bench.py
+    // few particles over data far larger than L2 -> the grid-per-run kernels: every SM streams 1/n_SM of the item
+    // ONCE per sweep and accumulates for all particles (the HBM-bound regime; with more particles than ~16 the sweep
+    // is FP64-bound and a cluster per chain does as well)
+    const bool can_grid = model->datum_form && data && layout_P <= DRJ_GRID_MAXP &&
+                          (model->jit ? (s->jf->grid_sweep_cu != nullptr && g_drv.LaunchCooperativeKernel != nullptr)
+                                      : model->grid_sweep_fn != nullptr);
+    bool want_grid = longest >= (1LL << 20) && layout_P <= 16;
+    if (cfg->flags & DRJ_FLAG_GRID_KERNEL) want_grid = true;
+    if (cfg->flags & (DRJ_FLAG_NO_GRID_KERNEL | DRJ_FLAG_TEAM_KERNEL)) want_grid = false;
+    if (const char* e = getenv("DRJ_GRID")) want_grid = (e[0] == '1') ? true : (e[0] == '0' ? false : want_grid);
+    if (can_grid && want_grid) {
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+      if (coop) {
+        s->gridk = true;
+        s->stream_variant = false;
+        if (const char* e = getenv("DRJ_GRID_STAGES")) grid_stages = std::max(2, std::min(DRJ_GRID_MAXSTAGES, atoi(e)));
+        s->cpc = C;
+        s->nthreads = DRJ_NT;
+      }
+    }
+    const bool can = !s->gridk && model->datum_form && data && R <= DRJ_TEAM_MAXR &&
+                     (model->jit ? (s->jf->team_sweep_cu != nullptr && g_drv.LaunchKernelEx != nullptr) : model->team_sweep_fn != nullptr);
+    bool want = longest > 2LL * DRJ_TILE && layout_P <= 4096;  // measured cross-over, tools/team_bench.py
     if (cfg->flags & DRJ_FLAG_TEAM_KERNEL) want = true;
     if (cfg->flags & DRJ_FLAG_NO_TEAM_KERNEL) want = false;
     if (const char* e = getenv("DRJ_TEAM")) want = (e[0] == '1') ? true : (e[0] == '0' ? false : want);
@@ -1172,6 +1394,13 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
       int rc = team_configure(s, err);
       if (rc) return rc;
       s->grid = C * s->team_ctas;
+    } else if (s->gridk) {
+      s->dyn_smem = (unsigned)(((long long)grid_stages * DRJ_GRID_CHUNK + 8) * sizeof(double));
+      int rc = grid_configure(s, err);
+      if (rc) return rc;
+    } else {
+      int rc = solo_configure(s, err);
+      if (rc) return rc;
     }
   }
 
@@ -1187,11 +1416,16 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     // update phase is long compared with the walk (measured: K4 +6 %, the 2-parameter n = 100 sweep -6 %).
     int d_free_n = 0;
     for (int i = 0; i < D; ++i) d_free_n += cfg->skip_param[i] ? 0 : 1;
-    a.warp_local = (32 % R == 0 && !streamed && !s->stream_variant && !s->team && 6 * d_free_n > R - 1) ? 1 : 0;
-    if (const char* e = getenv("DRJ_WARP_LOCAL")) if (e[0] == '1' && 32 % R == 0 && !streamed && !s->stream_variant && !s->team) a.warp_local = 1;
+    // (a per-datum model with several blocks never keeps its data resident: its sweeps take the tile path with
+    // CTA-wide barriers and a single producer thread, so its warps must not run ahead of each other)
+    const bool cta_wide = streamed || s->stream_variant || s->team || s->gridk || (model->datum_form && model->NBLOCK > 1);
+    a.warp_local = (32 % R == 0 && !cta_wide && 6 * d_free_n > R - 1) ? 1 : 0;
+    if (const char* e = getenv("DRJ_WARP_LOCAL")) if (e[0] == '1' && 32 % R == 0 && !cta_wide) a.warp_local = 1;
     if (const char* e = getenv("DRJ_NO_WARP_LOCAL")) if (e[0] == '1') a.warp_local = 0;
   }
   a.chains = C; a.rungs = R; a.chains_per_cta = s->cpc; a.team_ctas = s->team_ctas; a.team_stages = team_stages; a.coupling_on = cfg->coupling_on ? 1 : 0;
+  a.grid_stages = grid_stages;
+  a.grid_slots = (int)std::max<long long>(1, DRJ_NT / std::max<long long>(1, layout_P));  // from the whole run's size: shards stay bit-identical
   a.save_hot_draws = cfg->save_hot_draws ? 1 : 0; a.store_pt = cfg->store_pt ? 1 : 0;
   a.rng_mode = cfg->rng_mode; a.d_free = s->d_free;
   a.use_tma = (cfg->flags & DRJ_FLAG_NO_TMA) ? 0 : 1;
@@ -1234,6 +1468,11 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   CUDA_TRY(dalloc(s, &a.err_theta, (size_t)D * P));
   CUDA_TRY(dalloc(s, &s->err_key, 1));
   a.err_key = s->err_key;
+  if (s->gridk) {
+    CUDA_TRY(dalloc(s, &a.grid_part, (size_t)2 * DRJ_GRID_VRANKS * P));
+    CUDA_TRY(dalloc(s, &s->grid_bar, 1));
+    a.grid_bar = s->grid_bar;
+  }
   CUDA_TRY(cudaMemsetAsync(a.err_code, 0, sizeof(int) * (size_t)P, s->stream));
   CUDA_TRY(cudaMemsetAsync(s->err_key, 0xFF, sizeof(unsigned long long), s->stream));
   // ---- rings and final outputs
@@ -1251,7 +1490,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   a.n_iter = 1; a.iter0 = 0;
   CUDA_TRY(dalloc(s, &a.init_llb, (size_t)B * C));
   CUDA_TRY(dalloc(s, &a.init_lp, (size_t)C));
-  int rc = s->team ? DRJ_OK : launch_init_chain(s, err);
+  int rc = (s->team || s->gridk) ? DRJ_OK : launch_init_chain(s, err);
   if (rc) return rc;
   rc = launch_model_kernel(s, false, err);
   if (rc) return rc;
@@ -1336,7 +1575,127 @@ extern "C" int drj_session_timing(const drj_session* s, double* sweep_ms_total, 
   return DRJ_OK;
 }
 
-extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* err) {
+// D = -2 loglike over `C` chains of `S` draws each: mean and sample variance from the per-chain moments, chains in order
+static void deviance_from_chain_moments(const double* lm, const double* lv, long long C, int S, double* out2) {
+  const long long N = C * S;
+  double gm = 0.0;
+  for (long long c = 0; c < C; ++c) gm += lm[c];
+  gm /= (double)C;
+  double m2 = 0.0;
+  for (long long c = 0; c < C; ++c) m2 += lv[c] * (S - 1) + (double)S * (lm[c] - gm) * (lm[c] - gm);
+  out2[0] = -2.0 * gm;
+  out2[1] = N > 1 ? 4.0 * m2 / (double)(N - 1) : 0.0;
+}
+
+// ---- quantile select, shared by the one-device and the multi-device summaries
+struct QTarget { int param; long long rank; unsigned long long prefix; long long below; };  // `below` = draws with a smaller prefix
+
+// one histogram pass on one device: groups = distinct (param, prefix) pairs, ordered by param
+static int session_quantile_pass(drj_session* s, int bits_done, int nbits, const std::vector<unsigned long long>& prefix,
+                                 const std::vector<int>& group_ptr, std::vector<unsigned long long>& hist, drj_error* err) {
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  const int D = s->D, C = s->C, S = s->cfg.samples;
+  const int thR = s->cfg.save_hot_draws ? s->R : 1;
+  const double* th = s->fin_th_s + (long long)(thR - 1) * S * D;
+  const long long th_cs = (long long)thR * S * D, th_ts = D;
+  const int ng = (int)prefix.size();
+  int max_per_param = 0;
+  for (int k = 0; k < D; ++k) max_per_param = std::max(max_per_param, group_ptr[k + 1] - group_ptr[k]);
+  double *d_prefix = nullptr, *d_ptr = nullptr, *d_hist = nullptr;
+  CUDA_TRY(scratch_get(s, 9, sizeof(unsigned long long) * (size_t)std::max(ng, 1), &d_prefix));
+  CUDA_TRY(scratch_get(s, 10, sizeof(int) * (size_t)(D + 1), &d_ptr));
+  CUDA_TRY(scratch_get(s, 11, sizeof(unsigned long long) * (size_t)std::max(ng, 1) * DRJ_QBINS, &d_hist));
+  CUDA_TRY(cudaMemcpyAsync(d_prefix, prefix.data(), sizeof(unsigned long long) * (size_t)ng, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemcpyAsync(d_ptr, group_ptr.data(), sizeof(int) * (size_t)(D + 1), cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)ng * DRJ_QBINS, s->stream));
+  const size_t smem = sizeof(unsigned int) * (size_t)max_per_param * DRJ_QBINS;
+  CUDA_TRY(cudaFuncSetAttribute(drj_quantile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 49152)));
+  const int per_sm = smem > 100 * 1024 ? 1 : 2;
+  const int nb = std::max(1, std::min(C, prop_sms(s) * per_sm));
+  for (int k0 = 0; k0 < D; k0 += 65535) {
+    const int nk = std::min(D - k0, 65535);
+    drj_quantile_hist<<<dim3(nb, nk), 256, smem, s->stream>>>(th + k0, th_cs, th_ts, S, C, bits_done, nbits, (const unsigned long long*)d_prefix,
+                                                             (const int*)d_ptr + k0, (unsigned long long*)d_hist);
+    s->aux_launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  hist.assign((size_t)ng * DRJ_QBINS, 0ULL);
+  CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * hist.size(), cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return DRJ_OK;
+}
+
+// R's quantile(x, probs) (type 7: h = (N - 1) p, x[floor h] + (h - floor h)(x[floor h + 1] - x[floor h])) of every
+// parameter over all draws of all sessions; `pass` runs one histogram pass on every session and returns the sum
+template <class PassFn>
+static int select_quantiles(int D, long long N, const double* probs, int nq, double* out, PassFn pass, drj_error* err) {
+  if (nq <= 0 || !probs || !out) return DRJ_OK;
+  if (nq > 8) return set_err(err, DRJ_ERR_ARG, "at most 8 quantile probabilities per call");
+  for (int j = 0; j < nq; ++j)
+    if (!(probs[j] >= 0.0 && probs[j] <= 1.0)) return set_err(err, DRJ_ERR_ARG, "quantile probabilities must be in [0,1]");
+  std::vector<QTarget> tg;  // two order statistics per probability
+  std::vector<double> frac((size_t)nq);
+  for (int k = 0; k < D; ++k)
+    for (int j = 0; j < nq; ++j) {
+      const double h = (double)(N - 1) * probs[j];
+      const long long lo = (long long)std::floor(h);
+      frac[j] = h - (double)lo;
+      tg.push_back({k, lo, 0ULL, 0});
+      tg.push_back({k, std::min(lo + 1, N - 1), 0ULL, 0});
+    }
+  static const int digit_bits[6] = {11, 11, 11, 11, 11, 9};
+  int bits_done = 0;
+  for (int pass_i = 0; pass_i < 6; ++pass_i) {
+    const int nbits = digit_bits[pass_i];
+    // distinct (param, prefix) groups, ordered by parameter
+    std::vector<unsigned long long> prefix;
+    std::vector<int> group_ptr((size_t)D + 1, 0), group_of(tg.size(), -1);
+    for (int k = 0; k < D; ++k) {
+      group_ptr[k] = (int)prefix.size();
+      for (size_t i = 0; i < tg.size(); ++i) {
+        if (tg[i].param != k) continue;
+        int g = -1;
+        for (int q = group_ptr[k]; q < (int)prefix.size(); ++q) if (prefix[q] == tg[i].prefix) { g = q; break; }
+        if (g < 0) { g = (int)prefix.size(); prefix.push_back(tg[i].prefix); }
+        group_of[i] = g;
+      }
+    }
+    group_ptr[D] = (int)prefix.size();
+    std::vector<unsigned long long> hist;
+    int rc = pass(bits_done, nbits, prefix, group_ptr, hist);
+    if (rc) return rc;
+    for (size_t i = 0; i < tg.size(); ++i) {
+      const unsigned long long* h = hist.data() + (size_t)group_of[i] * DRJ_QBINS;
+      long long cum = tg[i].below;
+      int bin = 0;
+      const int nbins = 1 << nbits;
+      for (; bin < nbins; ++bin) {
+        if (cum + (long long)h[bin] > tg[i].rank) break;
+        cum += (long long)h[bin];
+      }
+      if (bin == nbins) return set_err(err, DRJ_ERR_CUDA, "quantile select lost rank %lld (histogram total %lld)", tg[i].rank, cum);
+      tg[i].below = cum;
+      tg[i].prefix = (tg[i].prefix << nbits) | (unsigned long long)bin;
+    }
+    bits_done += nbits;
+  }
+  auto value_of = [](unsigned long long key) {
+    const unsigned long long b = (key >> 63) ? (key & 0x7fffffffffffffffULL) : ~key;
+    double v;
+    memcpy(&v, &b, sizeof(v));
+    return v;
+  };
+  for (int k = 0; k < D; ++k)
+    for (int j = 0; j < nq; ++j) {
+      const double lo = value_of(tg[(size_t)(k * nq + j) * 2].prefix), hi = value_of(tg[(size_t)(k * nq + j) * 2 + 1].prefix);
+      out[(size_t)k * nq + j] = lo + frac[j] * (hi - lo);
+    }
+  return DRJ_OK;
+}
+
+// everything but the quantiles; lm_out / lv_out (may be NULL) receive the per-chain mean and variance of the
+// cold-rung sampling log-likelihood, from which the deviance moments of any set of chains follow exactly
+static int session_summary_core(drj_session* s, drj_summary* sm, std::vector<double>* lm_out, std::vector<double>* lv_out, drj_error* err) {
   if (!s || !sm) return set_err(err, DRJ_ERR_ARG, "NULL session or summary");
   if (sm->max_lag < 0 || sm->max_lag > 4096) return set_err(err, DRJ_ERR_ARG, "max_lag must be in [0, 4096]");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
@@ -1367,13 +1726,14 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   SUM_TRY(scratch_get(s, 6, sizeof(double) * (size_t)D, &d_ctr));
   // only what the caller asked for (each part is a pass over the stored draws)
   const bool want_theta_moments = sm->chain_mean || sm->chain_var || (sm->autocov_sum && !sm->center);
+  const bool want_dev = sm->deviance_mean_var || lm_out || lv_out;
   if (want_theta_moments) {
     drj_chain_moments<<<dim3(C, D), 256, 0, s->stream>>>(th, th_cs, th_ts, 1, S, D, d_mean, d_var);
     s->aux_launches++;
     SUM_TRY(cudaMemcpyAsync(mean.data(), d_mean, sizeof(double) * mean.size(), cudaMemcpyDeviceToHost, s->stream));
     SUM_TRY(cudaMemcpyAsync(var.data(), d_var, sizeof(double) * var.size(), cudaMemcpyDeviceToHost, s->stream));
   }
-  if (sm->deviance_mean_var) {
+  if (want_dev) {
     drj_chain_moments<<<dim3(C, 1), 256, 0, s->stream>>>(ll, ll_cs, 1, 0, S, 1, d_lm, d_lv);
     s->aux_launches++;
     SUM_TRY(cudaMemcpyAsync(lm.data(), d_lm, sizeof(double) * lm.size(), cudaMemcpyDeviceToHost, s->stream));
@@ -1382,16 +1742,9 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   SUM_TRY(cudaStreamSynchronize(s->stream));
   if (sm->chain_mean) memcpy(sm->chain_mean, mean.data(), sizeof(double) * mean.size());
   if (sm->chain_var) memcpy(sm->chain_var, var.data(), sizeof(double) * var.size());
-  if (sm->deviance_mean_var) {
-    // D = -2 loglike over all chains: mean and sample variance from the per-chain moments (equal lengths)
-    double gm = 0.0;
-    for (int c = 0; c < C; ++c) gm += lm[c];
-    gm /= C;
-    double m2 = 0.0;
-    for (int c = 0; c < C; ++c) m2 += lv[c] * (S - 1) + (double)S * (lm[c] - gm) * (lm[c] - gm);
-    sm->deviance_mean_var[0] = -2.0 * gm;
-    sm->deviance_mean_var[1] = N > 1 ? 4.0 * m2 / (double)(N - 1) : 0.0;
-  }
+  if (lm_out) *lm_out = lm;
+  if (lv_out) *lv_out = lv;
+  if (sm->deviance_mean_var) deviance_from_chain_moments(lm.data(), lv.data(), C, S, sm->deviance_mean_var);
   if (sm->autocov_sum) {
     for (int k = 0; k < D; ++k) {
       if (sm->center) ctr[k] = sm->center[k];
@@ -1427,6 +1780,17 @@ extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* e
   SUM_TRY(cudaGetLastError());
 #undef SUM_TRY
   return DRJ_OK;
+}
+
+extern "C" int drj_session_summary(drj_session* s, drj_summary* sm, drj_error* err) {
+  int rc = session_summary_core(s, sm, nullptr, nullptr, err);
+  if (rc) return rc;
+  if (sm->n_quantiles > 0 && sm->quantiles) {
+    auto pass = [&](int bits_done, int nbits, const std::vector<unsigned long long>& prefix, const std::vector<int>& group_ptr,
+                    std::vector<unsigned long long>& hist) { return session_quantile_pass(s, bits_done, nbits, prefix, group_ptr, hist, err); };
+    rc = select_quantiles(s->D, (long long)s->C * s->cfg.samples, sm->quantile_probs, sm->n_quantiles, sm->quantiles, pass, err);
+  }
+  return rc;
 }
 
 // draws to the host; thin > 1 keeps the stored iterations 0, thin, 2 thin, ... of every series (gathered on the
@@ -1521,6 +1885,280 @@ extern "C" int drj_run_mcmc(const drj_config* cfg, const drj_model* model, const
   }
   if (rc == DRJ_OK) rc = drj_session_download(s, out, err);
   drj_session_destroy(s);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one process, several GPUs (replaces the PSOCK-cluster dispatch of R/main.R:392-402)
+// ------------------------------------------------------------------------------------------------
+struct drj_multi {
+  drj_config cfg;                       // the whole run
+  std::vector<int> devices;             // one per shard
+  std::vector<int> first;               // first chain of shard k; first[n] = chains
+  std::vector<drj_session*> sessions;
+  int D = 0, R = 0;
+  long long U = 0, T = 0;
+  double t_create = 0.0;
+};
+
+// run fn(k) for every shard on its own host thread (shard 0 on the calling thread); returns the error of the shard
+// whose failure comes first in the reference's order (lowest iteration, then lowest chain)
+template <class Fn>
+static int for_each_shard(int n, drj_error* err, Fn fn) {
+  std::vector<int> rc((size_t)n, DRJ_OK);
+  std::vector<drj_error> errs((size_t)n);
+  for (auto& e : errs) memset(&e, 0, sizeof(e));
+  std::vector<std::thread> th;
+  for (int k = 1; k < n; ++k) th.emplace_back([&, k] { rc[k] = fn(k, &errs[k]); });
+  rc[0] = fn(0, &errs[0]);
+  for (auto& t : th) t.join();
+  int best = -1;
+  for (int k = 0; k < n; ++k) {
+    if (rc[k] == DRJ_OK) continue;
+    if (best < 0 || errs[k].iteration < errs[best].iteration ||
+        (errs[k].iteration == errs[best].iteration && errs[k].chain < errs[best].chain))
+      best = k;
+  }
+  if (best < 0) return DRJ_OK;
+  if (err) *err = errs[best];
+  return rc[best];
+}
+
+static void shard_output(const drj_multi* m, int k, int thin, const drj_output* out, drj_output* o) {
+  const drj_config& c = m->cfg;
+  const long long c0 = m->first[k];
+  const long long ptR = c.store_pt ? c.rungs : 1, thR = c.save_hot_draws ? c.rungs : 1;
+  const long long nb = (c.burnin + thin - 1) / thin, ns = (c.samples + thin - 1) / thin;
+  memset(o, 0, sizeof(*o));
+#define OFF(field, stride) o->field = out->field ? out->field + c0 * (stride) : nullptr
+  OFF(loglike_burnin, ptR * nb); OFF(logprior_burnin, ptR * nb); OFF(theta_burnin, thR * nb * c.d);
+  OFF(loglike_sampling, ptR * ns); OFF(logprior_sampling, ptR * ns); OFF(theta_sampling, thR * ns * c.d);
+  OFF(mc_accept_burnin, (long long)(c.rungs - 1)); OFF(mc_accept_sampling, (long long)(c.rungs - 1));
+  OFF(accept_burnin, (long long)c.rungs); OFF(accept_sampling, (long long)c.rungs);
+  OFF(t_diff, 1LL); OFF(bw_final, (long long)c.rungs * c.d);
+#undef OFF
+}
+
+extern "C" void drj_multi_destroy(drj_multi* m) {
+  if (!m) return;
+  for (drj_session* s : m->sessions) drj_session_destroy(s);
+  delete m;
+}
+
+extern "C" int drj_multi_device_count(const drj_multi* m) { return m ? (int)m->sessions.size() : 0; }
+
+extern "C" int drj_multi_create(const drj_config* cfg, const int32_t* devices, int32_t n_devices, const drj_model* model,
+                                const drj_list* data, const drj_list* misc, drj_multi** out, drj_error* err) {
+  if (err) memset(err, 0, sizeof(*err));
+  if (!out) return set_err(err, DRJ_ERR_ARG, "NULL out");
+  *out = nullptr;
+  int rc = validate(cfg, model, data, err);
+  if (rc) return rc;
+  std::vector<int> devs;
+  if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+  else {
+    const int n = drj_device_count();
+    if (n < 1) return set_err(err, DRJ_ERR_CUDA, "no CUDA device");
+    for (int i = 0; i < n; ++i) devs.push_back(i);
+  }
+  const int visible = drj_device_count();
+  // (a device may be listed more than once: its chain ranges then run side by side on it)
+  for (size_t i = 0; i < devs.size(); ++i)
+    if (devs[i] < 0 || devs[i] >= visible) return set_err(err, DRJ_ERR_CUDA, "no CUDA device %d", devs[i]);
+  const int n = (int)std::min<long long>((long long)devs.size(), cfg->chains);  // no empty shards: spare devices stay idle
+  drj_multi* m = new drj_multi();
+  m->cfg = *cfg;
+  m->t_create = wall_now();
+  m->D = cfg->d; m->R = cfg->rungs;
+  m->devices.assign(devs.begin(), devs.begin() + n);
+  m->first.resize((size_t)n + 1);
+  for (int k = 0; k <= n; ++k) {  // contiguous ranges, sizes differing by at most one
+    const long long base = cfg->chains / n, rem = cfg->chains % n;
+    m->first[k] = (int)(k * base + std::min<long long>(k, rem));
+  }
+  int d_free = 0;
+  for (int i = 0; i < cfg->d; ++i) d_free += cfg->skip_param[i] ? 0 : 1;
+  m->U = 3LL * d_free * cfg->rungs + ((cfg->coupling_on && cfg->rungs > 1) ? (cfg->rungs - 1) : 0);
+  m->T = cfg->burnin - 1 + cfg->samples;
+  m->sessions.assign((size_t)n, nullptr);
+  rc = for_each_shard(n, err, [&](int k, drj_error* e) {
+    drj_config c = *cfg;
+    c.device = m->devices[k];
+    c.chains = m->first[k + 1] - m->first[k];
+    c.chain_offset = cfg->chain_offset + m->first[k];
+    c.layout_chains = std::max(cfg->layout_chains, cfg->chains);
+    c.theta_init = cfg->theta_init + (long long)m->first[k] * cfg->d;
+    if (cfg->rng_mode == DRJ_RNG_REPLAY) c.replay_uniforms = cfg->replay_uniforms + (long long)m->first[k] * m->T * m->U;
+    return drj_session_create(&c, model, data, misc, &m->sessions[k], e);
+  });
+  if (rc) { drj_multi_destroy(m); return rc; }
+  *out = m;
+  return DRJ_OK;
+}
+
+extern "C" int drj_multi_advance(drj_multi* m, int n_iter, float* kernel_ms, drj_error* err) {
+  if (!m) return set_err(err, DRJ_ERR_ARG, "NULL multi-device run");
+  const int n = (int)m->sessions.size();
+  std::vector<float> ms((size_t)n, 0.f);
+  int rc = for_each_shard(n, err, [&](int k, drj_error* e) { return drj_session_advance(m->sessions[k], n_iter, &ms[k], e); });
+  if (kernel_ms) *kernel_ms = *std::max_element(ms.begin(), ms.end());
+  return rc;
+}
+
+extern "C" int drj_multi_download_thinned(drj_multi* m, int thin, drj_output* out, drj_error* err) {
+  if (!m || !out) return set_err(err, DRJ_ERR_ARG, "NULL multi-device run or output");
+  if (thin < 1) return set_err(err, DRJ_ERR_ARG, "thin must be >= 1");
+  int rc = for_each_shard((int)m->sessions.size(), err, [&](int k, drj_error* e) {
+    drj_output o;
+    shard_output(m, k, thin, out, &o);
+    return drj_session_download_thinned(m->sessions[k], thin, &o, e);
+  });
+  if (rc == DRJ_OK && out->t_diff) {  // whole-call wall time / chains, as the one-device entry reports it
+    const double dt = (wall_now() - m->t_create) / std::max(1, m->cfg.chains);
+    for (int ch = 0; ch < m->cfg.chains; ++ch) out->t_diff[ch] = dt;
+  }
+  return rc;
+}
+
+extern "C" int drj_multi_launches(const drj_multi* m, int64_t* sweep_launches, int64_t* aux_launches) {
+  if (!m) return DRJ_ERR_ARG;
+  int64_t a = 0, b = 0;
+  for (const drj_session* s : m->sessions) { a += s->sweep_launches; b += s->aux_launches; }
+  if (sweep_launches) *sweep_launches = a;
+  if (aux_launches) *aux_launches = b;
+  return DRJ_OK;
+}
+
+extern "C" int drj_multi_summary(drj_multi* m, drj_summary* sm, drj_error* err) {
+  if (!m || !sm) return set_err(err, DRJ_ERR_ARG, "NULL multi-device run or summary");
+  if (sm->max_lag < 0 || sm->max_lag > 4096) return set_err(err, DRJ_ERR_ARG, "max_lag must be in [0, 4096]");
+  const int n = (int)m->sessions.size(), D = m->D, L = sm->max_lag, S = m->cfg.samples;
+  const long long C = m->cfg.chains;
+  // ---- pass 1: per-chain moments of theta and of the log-likelihood, every device into its slice
+  const bool need_mean = sm->chain_mean || sm->chain_var || (sm->autocov_sum && !sm->center);
+  std::vector<double> mean, var, lm((size_t)C), lv((size_t)C);
+  if (need_mean) { mean.resize((size_t)C * D); var.resize((size_t)C * D); }
+  const bool want_dev = sm->deviance_mean_var != nullptr;
+  if (need_mean || want_dev) {
+    int rc = for_each_shard(n, err, [&](int k, drj_error* e) {
+      drj_summary one;
+      memset(&one, 0, sizeof(one));
+      if (need_mean) { one.chain_mean = mean.data() + (size_t)m->first[k] * D; one.chain_var = var.data() + (size_t)m->first[k] * D; }
+      std::vector<double> a, b;
+      int r = session_summary_core(m->sessions[k], &one, want_dev ? &a : nullptr, want_dev ? &b : nullptr, e);
+      if (r == DRJ_OK && want_dev) {
+        std::copy(a.begin(), a.end(), lm.begin() + m->first[k]);
+        std::copy(b.begin(), b.end(), lv.begin() + m->first[k]);
+      }
+      return r;
+    });
+    if (rc) return rc;
+  }
+  if (sm->chain_mean) memcpy(sm->chain_mean, mean.data(), sizeof(double) * mean.size());
+  if (sm->chain_var) memcpy(sm->chain_var, var.data(), sizeof(double) * var.size());
+  if (want_dev) deviance_from_chain_moments(lm.data(), lv.data(), C, S, sm->deviance_mean_var);
+  // ---- pass 2: autocovariance sums about the GLOBAL centre (the same expression as the one-device path: mean of the
+  // chain means in chain order), added over the devices in shard order, plus the lag products that straddle two shards
+  if (sm->autocov_sum || ((sm->head || sm->tail) && L > 0)) {
+    std::vector<double> ctr((size_t)D, 0.0);
+    for (int k = 0; k < D; ++k) {
+      if (sm->center) ctr[k] = sm->center[k];
+      else if (!mean.empty()) { double t = 0.0; for (long long c = 0; c < C; ++c) t += mean[(size_t)c * D + k]; ctr[k] = t / (double)C; }
+    }
+    const size_t nac = (size_t)D * (L + 1), nht = (size_t)D * std::max(L, 1);
+    std::vector<double> ac((size_t)n * nac, 0.0), hd((size_t)n * nht, 0.0), tl((size_t)n * nht, 0.0);
+    int rc = for_each_shard(n, err, [&](int k, drj_error* e) {
+      drj_summary one;
+      memset(&one, 0, sizeof(one));
+      one.max_lag = L;
+      one.center = ctr.data();
+      if (sm->autocov_sum) one.autocov_sum = ac.data() + (size_t)k * nac;
+      if (L > 0) { one.head = hd.data() + (size_t)k * nht; one.tail = tl.data() + (size_t)k * nht; }
+      return session_summary_core(m->sessions[k], &one, nullptr, nullptr, e);
+    });
+    if (rc) return rc;
+    if (sm->autocov_sum) {
+      for (size_t i = 0; i < nac; ++i) {
+        double t = 0.0;
+        for (int k = 0; k < n; ++k) t += ac[(size_t)k * nac + i];
+        sm->autocov_sum[i] = t;
+      }
+      // x_j among the last `lag` draws of shard k pairs with x_{j+lag} among the first `lag` draws of shard k+1
+      // (a shard holds at least `samples` >= 1 draws; lags longer than a shard would reach a third shard: the
+      // concatenated window below covers that too)
+      for (int p = 0; p < D && L > 0; ++p)
+        for (int k = 0; k + 1 < n; ++k) {
+          // window = last min(L, len_k) draws of shards <= k (walking back) | first min(L, len) draws of shards > k
+          std::vector<double> left, right;
+          for (int q = k; q >= 0 && (int)left.size() < L; --q) {
+            const long long len = (long long)(m->first[q + 1] - m->first[q]) * S;
+            const int take = (int)std::min<long long>(L - (long long)left.size(), std::min<long long>(len, L));
+            const double* t = tl.data() + (size_t)q * nht + (size_t)p * L;  // last L draws of shard q (zero-padded at the front if shorter)
+            for (int i = 0; i < take; ++i) left.push_back(t[L - 1 - i] - ctr[p]);  // reversed: left[0] is the draw just before the boundary
+          }
+          for (int q = k + 1; q < n && (int)right.size() < L; ++q) {
+            const long long len = (long long)(m->first[q + 1] - m->first[q]) * S;
+            const int take = (int)std::min<long long>(L - (long long)right.size(), std::min<long long>(len, L));
+            const double* h = hd.data() + (size_t)q * nht + (size_t)p * L;
+            for (int i = 0; i < take; ++i) right.push_back(h[i] - ctr[p]);
+          }
+          // pairs (left[a], right[b]) at lag a + b + 1; only pairs whose LEFT element lies in shard k itself are new at
+          // this boundary (pairs reaching further back are counted at the earlier boundary)
+          const long long len_k = (long long)(m->first[k + 1] - m->first[k]) * S;
+          const int own = (int)std::min<long long>((long long)left.size(), len_k);
+          for (int a = 0; a < own; ++a)
+            for (int b = 0; b < (int)right.size() && a + b + 1 <= L; ++b)
+              sm->autocov_sum[(size_t)p * (L + 1) + a + b + 1] += left[a] * right[b];
+        }
+    }
+    if (L > 0) {  // ends of the whole concatenated series (for a caller that shards further, e.g. over nodes)
+      if (sm->head) memcpy(sm->head, hd.data(), sizeof(double) * nht);
+      if (sm->tail) memcpy(sm->tail, tl.data() + (size_t)(n - 1) * nht, sizeof(double) * nht);
+    }
+  }
+  // ---- quantiles: radix select with the histograms of all devices added per pass
+  if (sm->n_quantiles > 0 && sm->quantiles) {
+    auto pass = [&](int bits_done, int nbits, const std::vector<unsigned long long>& prefix, const std::vector<int>& group_ptr,
+                    std::vector<unsigned long long>& hist) {
+      std::vector<std::vector<unsigned long long>> part((size_t)n);
+      int rc = for_each_shard(n, err, [&](int k, drj_error* e) {
+        return session_quantile_pass(m->sessions[k], bits_done, nbits, prefix, group_ptr, part[k], e);
+      });
+      if (rc) return rc;
+      hist.assign(part[0].size(), 0ULL);
+      for (int k = 0; k < n; ++k)
+        for (size_t i = 0; i < hist.size(); ++i) hist[i] += part[k][i];
+      return (int)DRJ_OK;
+    };
+    int rc = select_quantiles(D, C * S, sm->quantile_probs, sm->n_quantiles, sm->quantiles, pass, err);
+    if (rc) return rc;
+  }
+  return DRJ_OK;
+}
+
+extern "C" int drj_run_mcmc_multi(const drj_config* cfg, const int32_t* devices, int32_t n_devices, const drj_model* model,
+                                  const drj_list* data, const drj_list* misc, drj_output* out, drj_progress_fn progress,
+                                  void* progress_user, drj_error* err) {
+  if (err) memset(err, 0, sizeof(*err));
+  if (!out) return set_err(err, DRJ_ERR_ARG, "NULL output");
+  drj_multi* m = nullptr;
+  int rc = drj_multi_create(cfg, devices, n_devices, model, data, misc, &m, err);
+  if (rc) return rc;
+  const int nb = cfg->burnin - 1;
+  // the progress hook runs here, on the calling thread, between batches (the worker threads of a batch have joined)
+  for (int phase = 0; phase < 2 && rc == DRJ_OK; ++phase) {
+    const int total = phase == 0 ? nb : cfg->samples;
+    const int step = progress ? std::max(1, (total + 99) / 100) : std::max(total, 1);
+    for (int done = 0; done < total && rc == DRJ_OK;) {
+      const int n = std::min(step, total - done);
+      rc = drj_multi_advance(m, n, nullptr, err);
+      done += n;
+      if (rc == DRJ_OK && progress && progress(progress_user, phase, done + (phase == 0 ? 1 : 0), phase == 0 ? cfg->burnin : cfg->samples))
+        rc = set_err(err, DRJ_ERR_INTERRUPT, "interrupted by the progress callback");
+    }
+  }
+  if (rc == DRJ_OK) rc = drj_multi_download_thinned(m, 1, out, err);
+  drj_multi_destroy(m);
   return rc;
 }
 

@@ -57,6 +57,8 @@ struct DrjKernelArgs {
   int warp_local;      // rungs divide 32 and nothing in the loop needs a CTA barrier: chains sync per warp
   int team_ctas;       // TEAM kernels: CTAs per cluster (one cluster per chain), 1..16
   int team_stages;     // TEAM kernels: depth of the TMA tile pipeline (tiles resident per CTA), 2..DRJ_TEAM_MAXSTAGES
+  int grid_slots;      // GRID kernels: data slots per particle in a CTA (threads slot * P + particle), fixed by the WHOLE run's size
+  int grid_stages;     // GRID kernels: depth of the TMA chunk pipeline, 2..DRJ_GRID_MAXSTAGES
   long long chain_offset;     // global id of chain 0 (Philox counter)
   unsigned long long seed;
   double target_acceptance;
@@ -95,6 +97,9 @@ struct DrjKernelArgs {
   // initial block likelihoods / prior of every chain (all rungs of a chain start from the same theta)
   double* init_llb;   // [B][chains]
   double* init_lp;    // [chains]
+  // GRID kernels: per-virtual-rank partial sums [2][DRJ_GRID_VRANKS][P] and the grid barrier counter (0 at launch)
+  double* grid_part;
+  unsigned int* grid_bar;
   // error slot
   unsigned long long* err_key;  // packed (iteration-in-launch, chain, rung, param), atomicMin
   int* err_code;                // [P] code of the particle's first error in this launch
@@ -127,6 +132,9 @@ __device__ __forceinline__ void drj_mbar_wait(unsigned long long* bar, unsigned 
       "}\n" ::"r"(drj_smem_addr(bar)),
       "r"(parity)
       : "memory");
+}
+__device__ __forceinline__ void drj_mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(drj_smem_addr(bar)) : "memory");
 }
 // 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`
 __device__ __forceinline__ void drj_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,
@@ -179,7 +187,7 @@ __device__ __forceinline__ void drj_st_cluster(double* local_smem_ptr, unsigned 
 
 template <class M, bool DF = M::DATUM_FORM>
 struct DrjTiles {  // no tiles for generic models
-  template <bool TEAM>
+  template <int MODE>
   __device__ __forceinline__ void init(const DrjKernelArgs&) {}
 };
 
@@ -202,10 +210,27 @@ __device__ __forceinline__ double* drj_tile_buf() {
 #ifndef DRJ_TEAM_NT
 #define DRJ_TEAM_NT 256        // TEAM kernels: threads per CTA (512, at a 128-register cap, measured 5-10 % slower on every shape)
 #endif
+// GRID kernels (few particles x data far larger than L2: the HBM-bound regime)
+#define DRJ_GRID_VRANKS 1184   // canonical number of partial sums a data item is split into: 8 per SM of a 148-SM B200
+#ifndef DRJ_GRID_CHUNK
+#define DRJ_GRID_CHUNK 2048    // doubles per TMA chunk (16 KB)
+#endif
+#define DRJ_GRID_MAXSTAGES 12  // at most this many chunks in flight per CTA
+#define DRJ_GRID_MAXP 256      // at most this many particles (chains x rungs): every CTA holds a replica of each
+// kernel families: one thread per particle / one cluster per chain / the whole grid per run
+#define DRJ_MODE_SOLO 0
+#define DRJ_MODE_TEAM 1
+#define DRJ_MODE_GRID 2
 template <class M>
 __device__ __forceinline__ unsigned long long* drj_tile_bars() {
   __shared__ __align__(8) unsigned long long s_full[DRJ_TEAM_MAXSTAGES];
   return s_full;
+}
+// GRID: "stage consumed" barriers (one arrival per warp), so that only the producer thread ever waits for the slowest warp
+template <class M>
+__device__ __forceinline__ unsigned long long* drj_tile_empty_bars() {
+  __shared__ __align__(8) unsigned long long s_empty[DRJ_GRID_MAXSTAGES];
+  return s_empty;
 }
 // TEAM kernels: per-thread partials of the CTA reduction, and the all-gathered partial sums
 // [parity][virtual rank][rung] every CTA of the cluster receives from its peers
@@ -223,24 +248,34 @@ __device__ __forceinline__ double* drj_team_part() {
 template <class M>
 struct DrjTiles<M, true> {
   unsigned ph0, ph1;           // phase parity of each stage
-  unsigned team_ph;            // TEAM: phase parity bit of every stage
-  unsigned team_pb;            // TEAM: which half of the all-gather buffer the next sweep uses
+  unsigned team_ph;            // TEAM / GRID: phase parity bit of every stage's "full" barrier (consumer side)
+  unsigned team_pb;            // TEAM / GRID: which half of the partial-sum buffer the next sweep uses
+  unsigned grid_eph;           // GRID, producer thread: phase parity bit of every stage's "empty" barrier
+  unsigned grid_epoch;         // GRID: grid barriers passed so far in this launch
+  int grid_cs, grid_ps;        // GRID: next stage to consume / to fill
+  int grid_pn;                 // GRID, producer thread: chunks requested so far in this launch
   bool resident;               // whole item lives in the tile buffer for the life of the kernel
   bool tma;
-  template <bool TEAM>
+  template <int MODE>
   __device__ __forceinline__ void init(const DrjKernelArgs& a) {
+    constexpr bool TEAM = MODE != DRJ_MODE_SOLO;  // (both cluster and grid kernels always stream)
     double* s_buf = drj_tile_buf<M>();
     unsigned long long* full = drj_tile_bars<M>();
     ph0 = ph1 = 0;
     team_ph = 0; team_pb = 0;
+    grid_eph = 0; grid_epoch = 0; grid_cs = 0; grid_ps = 0; grid_pn = 0;
     tma = a.use_tma != 0;
     // single-item models keep the data resident when it fits the two tiles
     const int item = M::datum_item(1);
     const long long n = a.data.len(item);
     resident = !TEAM && (M::NBLOCK == 1) && (n <= 2 * DRJ_TILE);
     if (threadIdx.x == 0) {
-      const int nbar = TEAM ? a.team_stages : 2;
+      const int nbar = MODE == DRJ_MODE_GRID ? a.grid_stages : (MODE == DRJ_MODE_TEAM ? a.team_stages : 2);
       for (int q = 0; q < nbar; ++q) drj_mbar_init(&full[q], 1);
+      if (MODE == DRJ_MODE_GRID) {
+        unsigned long long* empty = drj_tile_empty_bars<M>();
+        for (int q = 0; q < nbar; ++q) drj_mbar_init(&empty[q], blockDim.x >> 5);
+      }
       drj_mbar_fence_init();
     }
     if (resident) {
@@ -500,23 +535,183 @@ __device__ __forceinline__ double drj_sweep_item_team(DrjTiles<M, true>& T, cons
   return tot;
 }
 
-template <class M, bool TEAM>
+// ------------------------------------------------------------------ GRID sweep (few particles x data >> L2)
+// The HBM-bound regime (SURVEY 7.1-4 "for few chains x huge n, switch to split-n"): with a handful of particles
+// over a data item far larger than L2 the likelihood sum costs 8 bytes of HBM traffic per 2 P FP64 instructions,
+// and the only way to the HBM roofline is to read the item ONCE per sweep with every SM.  The GRID kernels run
+// the whole grid as one team: every CTA holds a replica of EVERY particle (thread tid < P replicates particle
+// tid = chain * R + rung; the update arithmetic is deterministic, so the replicas of all CTAs stay bit-identical
+// without communication, as in the TEAM kernels), and only the data sweep is divided:
+//   * the item is cut into chunks of DRJ_GRID_CHUNK doubles and the chunks, in order, into DRJ_GRID_VRANKS
+//     contiguous "virtual ranks" (fewer when the item has fewer chunks); CTA b of a G-CTA grid owns the
+//     contiguous virtual ranks [b V / G, (b + 1) V / G), i.e. one contiguous 1/G of the item;
+//   * the CTA streams its chunks through an NS-deep TMA pipeline (cp.async.bulk + one "full" mbarrier per stage;
+//     a stage is handed back through an "empty" mbarrier with one arrival per warp, and the producer thread
+//     refills the stage released one chunk earlier, so no warp but the producer's ever waits for another);
+//   * inside a chunk the thread (slot s, particle q) = tid s * P + q takes the 16-byte pairs s, s + S, ... and
+//     accumulates them for ITS particle's proposal (Consts published through shared memory): one pass over the
+//     data serves all P particles;
+//   * at the end of a virtual rank the S per-slot sums of every particle are combined in a fixed two-level order
+//     and written to global memory; ONE grid-wide barrier per sweep (co-residency is guaranteed by the
+//     cooperative launch); then every CTA sums the <= 1184 partials of every particle in the same fixed order
+//     (lane l takes v = l, l + 32, ... sequentially, xor-shuffle tree).
+// The association depends only on (n, S): results are bitwise independent of the grid size, the pipeline depth
+// and the launch split; S is derived from the WHOLE run's particle count (drj_config.layout_chains), so a shard
+// of a run reproduces its slice bit for bit.  HBM traffic: 8 n bytes per sweep for all particles together.
+__device__ __forceinline__ void drj_grid_barrier(unsigned int* bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // the CTA's partial sums (ordered before by the CTA barrier) become visible grid-wide
+    atomicAdd(bar, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+// first chunk of virtual rank v when `nchunks` chunks are dealt to `nv` ranks in contiguous, near-equal runs
+__device__ __forceinline__ long long drj_grid_first_chunk(long long v, long long nchunks, long long nv) {
+  return (v * nchunks) / nv;
+}
+
+// Must be called by every thread of every CTA of the grid (uniform control flow).  `own` = index of the particle
+// whose total this thread wants back (its own particle; shadow threads replicate a particle of chain 0).
+template <class M>
+__device__ __forceinline__ double drj_sweep_item_grid(DrjTiles<M, true>& T, const DrjKernelArgs& a,
+                                                      const typename M::Consts& kmine, int own,
+                                                      const double* __restrict__ g, long long n) {
+  __shared__ typename M::Consts s_consts[DRJ_GRID_MAXP];
+  __shared__ double s_l1[DRJ_NT];
+  double* const buf = drj_tile_buf<M>();
+  unsigned long long* const full = drj_tile_bars<M>();
+  unsigned long long* const empty = drj_tile_empty_bars<M>();
+  double* const s_red = drj_team_red<M>();
+  const int P = (int)a.P, S = a.grid_slots, NS = a.grid_stages;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int slot = tid / P, q = tid - slot * P;
+  const bool worker = slot < S;
+  double* const part = a.grid_part + (long long)T.team_pb * DRJ_GRID_VRANKS * P;
+  T.team_pb ^= 1u;  // slower CTAs may still be reading the other half (one grid barrier per sweep)
+
+  // every particle's proposal constants, published by the replica in slot 0
+  if (tid < P) s_consts[tid] = kmine;
+  __syncthreads();
+  typename M::Consts k;
+  if (worker) k = s_consts[q];
+
+  const long long nchunks = (n + DRJ_GRID_CHUNK - 1) / DRJ_GRID_CHUNK;
+  const long long nv = nchunks < DRJ_GRID_VRANKS ? nchunks : DRJ_GRID_VRANKS;
+  const long long G = gridDim.x, b = blockIdx.x;
+  const long long v_lo = (b * nv) / G, v_hi = ((b + 1) * nv) / G;
+  const long long c_lo = nv ? drj_grid_first_chunk(v_lo, nchunks, nv) : 0;
+  const long long c_hi = nv ? drj_grid_first_chunk(v_hi, nchunks, nv) : 0;
+  const int last_cnt = (int)(n - (nchunks - 1) * DRJ_GRID_CHUNK);  // data points in the item's last chunk
+
+  // producer (thread 0): chunk `pc` goes into stage T.grid_ps once the warps have handed that stage back
+  long long pc = c_lo;
+  auto produce = [&]() {
+    if (pc >= c_hi) return;
+    const int ps = T.grid_ps;
+    if (T.grid_pn >= NS) {
+      drj_mbar_wait(&empty[ps], (T.grid_eph >> ps) & 1u);
+      T.grid_eph ^= 1u << ps;
+    }
+    const int c = (pc == nchunks - 1) ? last_cnt : DRJ_GRID_CHUNK;
+    const unsigned bytes = (unsigned)((c + 1) & ~1) * (unsigned)sizeof(double);
+    drj_mbar_expect_tx(&full[ps], bytes);
+    drj_bulk_g2s(buf + ps * DRJ_GRID_CHUNK, g + pc * DRJ_GRID_CHUNK, bytes, &full[ps]);
+    ++pc;
+    ++T.grid_pn;
+    T.grid_ps = (ps + 1 == NS) ? 0 : ps + 1;
+  };
+  if (T.tma && tid == 0)
+    for (int j = 0; j < NS - 1; ++j) produce();
+
+  const int mine_full = worker ? drj_team_pairs(DRJ_GRID_CHUNK, slot, S) : 0;
+  // level-1 groups of the per-rank reduction: J groups of slots j, j + J, ... per particle
+  const int J = S < 16 ? S : 16;
+  long long c = c_lo;
+  for (long long v = v_lo; v < v_hi; ++v) {
+    const long long c_end = drj_grid_first_chunk(v + 1, nchunks, nv);
+    DrjAcc A;
+    A.zero();
+    for (; c < c_end; ++c) {
+      const int cnt = (c == nchunks - 1) ? last_cnt : DRJ_GRID_CHUNK;
+      if (T.tma) {
+        if (tid == 0) produce();  // refills the stage of chunk c - 1
+        const int cs = T.grid_cs;
+        drj_mbar_wait(&full[cs], (T.team_ph >> cs) & 1u);
+        T.team_ph ^= 1u << cs;
+        if (worker)
+          drj_team_accum<M>(k, buf + cs * DRJ_GRID_CHUNK, cnt, slot, S,
+                            cnt == DRJ_GRID_CHUNK ? mine_full : drj_team_pairs(cnt, slot, S), A);
+        __syncwarp();
+        if (lane == 0) drj_mbar_arrive(&empty[cs]);
+        T.grid_cs = (cs + 1 == NS) ? 0 : cs + 1;
+      } else {
+        __syncthreads();
+        for (int j = tid; j < cnt; j += blockDim.x) buf[j] = g[c * DRJ_GRID_CHUNK + j];
+        __syncthreads();
+        if (worker) drj_team_accum<M>(k, buf, cnt, slot, S, cnt == DRJ_GRID_CHUNK ? mine_full : drj_team_pairs(cnt, slot, S), A);
+      }
+    }
+    // the S slot sums of every particle, fixed two-level order: group j takes slots j, j + J, ... in sequence,
+    // then the J group sums in sequence
+    s_red[tid] = worker ? A.total() : 0.0;  // (the previous rank's reads of s_red / s_l1 are two CTA barriers back)
+    __syncthreads();
+    if (tid < P * J) {
+      const int qq = tid % P, j = tid / P;
+      double t = 0.0;
+      for (int s2 = j; s2 < S; s2 += J) t += s_red[s2 * P + qq];
+      s_l1[tid] = t;
+    }
+    __syncthreads();
+    if (tid < P) {
+      double t = 0.0;
+      for (int j = 0; j < J; ++j) t += s_l1[j * P + tid];
+      part[v * P + tid] = t;
+    }
+  }
+  ++T.grid_epoch;
+  drj_grid_barrier(a.grid_bar, T.grid_epoch * (unsigned)G);
+  // totals: warp w takes the particles w, w + nwarps, ...; lane l the partials l, l + 32, ... of the particle
+  {
+    const int nwarps = blockDim.x >> 5;
+    for (int qq = tid >> 5; qq < P; qq += nwarps) {
+      double t = 0.0;
+#pragma unroll 4
+      for (long long v = lane; v < nv; v += 32) t += __ldcg(&part[v * P + qq]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == 0) s_l1[qq] = t;
+    }
+  }
+  __syncthreads();
+  const double tot = s_l1[own];
+  __syncthreads();  // (s_l1 is reused by the next sweep)
+  return tot;
+}
+
+template <class M, int MODE>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const DrjKernelArgs& a,
-                                                   const double* theta, int block) {
+                                                   const double* theta, int block, int own) {
   typename M::Consts k;
   const bool fast = M::prepare(theta, a.misc, block, k);
   const int item = M::datum_item(block);
   const long long n = a.data.len(item);
   double acc;  // uniform: all threads sweep
-  if constexpr (TEAM) acc = drj_sweep_item_team<M>(T, a, k, a.data.item(item), n);
+  if constexpr (MODE == DRJ_MODE_GRID) acc = drj_sweep_item_grid<M>(T, a, k, own, a.data.item(item), n);
+  else if constexpr (MODE == DRJ_MODE_TEAM) acc = drj_sweep_item_team<M>(T, a, k, a.data.item(item), n);
   else acc = drj_sweep_item<M>(T, k, a.data.item(item), n);
   if (fast) return M::finish(k, acc, n);
   return M::loglike(theta, a.data, a.misc, block);  // degenerate theta: exact serial evaluation
 }
 
-template <class M, bool TEAM>
+template <class M, int MODE>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, false>&, const DrjKernelArgs& a,
-                                                   const double* theta, int block) {
+                                                   const double* theta, int block, int) {
   return M::loglike(theta, a.data, a.misc, block);
 }
 
@@ -595,7 +790,7 @@ __device__ __forceinline__ void drj_init_chain_body(const DrjKernelArgs& a) {
   const bool active = c < a.chains;
   const long long cc = active ? c : 0;  // inactive threads shadow chain 0 (uniform control flow)
   DrjTiles<M> T;
-  T.template init<false>(a);
+  T.template init<DRJ_MODE_SOLO>(a);
   double theta[D], llb[B];
   for (int i = 0; i < D; ++i) theta[i] = a.theta_init[cc * D + i];
 #pragma unroll UB
@@ -610,7 +805,7 @@ __device__ __forceinline__ void drj_init_chain_body(const DrjKernelArgs& a) {
         if ((seen >> (b - 1)) & 1ULL) continue;
         seen |= 1ULL << (b - 1);
       }
-      llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, false>(T, a, theta, b);
+      llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, DRJ_MODE_SOLO>(T, a, theta, b, 0);
     }
   const double lp = M::logprior(theta, a.misc);
   if (active) {
@@ -622,21 +817,24 @@ __device__ __forceinline__ void drj_init_chain_body(const DrjKernelArgs& a) {
 
 // TEAM: one cluster per chain, every thread a replica of rung (tid mod R); the replica in slot 0 of CTA 0
 // of the cluster (`active`) is the one that writes to HBM.
-template <class M, bool TEAM>
+// GRID: every CTA holds a replica of every particle (thread tid < P = particle tid); CTA 0's write to HBM.
+template <class M, int MODE>
 __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
+  constexpr bool TEAM = MODE == DRJ_MODE_TEAM, GRID = MODE == DRJ_MODE_GRID;
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
   const int R = a.rungs;
   const int tid = threadIdx.x;
   const int lc = tid / R, r = tid - lc * R;
-  const long long chain = TEAM ? (long long)drj_cluster_id_x() : (long long)blockIdx.x * a.chains_per_cta + lc;
-  const bool active = TEAM ? (lc == 0 && drj_cluster_ctarank() == 0u) : ((lc < a.chains_per_cta) && (chain < a.chains));
-  const long long cc = (TEAM || active) ? chain : 0;  // inactive threads shadow chain 0 (uniform control flow)
+  const long long chain = TEAM ? (long long)drj_cluster_id_x() : (GRID ? (long long)lc : (long long)blockIdx.x * a.chains_per_cta + lc);
+  const bool valid = TEAM || (GRID ? (chain < a.chains) : ((lc < a.chains_per_cta) && (chain < a.chains)));
+  const bool active = TEAM ? (lc == 0 && drj_cluster_ctarank() == 0u) : (valid && (!GRID || blockIdx.x == 0));
+  const long long cc = valid ? chain : 0;  // threads without a particle shadow chain 0 (uniform control flow)
   const long long p = cc * R + r;
   const long long P = a.P;
 
   DrjTiles<M> T;
-  if constexpr (TEAM) T.template init<TEAM>(a);
+  if constexpr (MODE != DRJ_MODE_SOLO) T.template init<MODE>(a);
 
   DrjState<M> s;
   int err = 0;
@@ -659,7 +857,7 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
   }
 #pragma unroll UB
   for (int b = 0; b < B; ++b) s.llb[b] = 0.0;
-  if constexpr (TEAM) {
+  if constexpr (MODE != DRJ_MODE_SOLO) {
     // init_like: every block listed by every parameter (duplicates re-evaluated), Particle.h:62-68
     // (a block listed by several parameters is evaluated once: same theta, same value)
     unsigned long long seen = 0ULL;
@@ -670,7 +868,7 @@ __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
           if ((seen >> (b - 1)) & 1ULL) continue;
           seen |= 1ULL << (b - 1);
         }
-        s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, TEAM>(T, a, s.theta, b);
+        s.llb[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, MODE>(T, a, s.theta, b, (int)p);
       }
     s.lp = M::logprior(s.theta, a.misc);
   } else {
@@ -735,17 +933,19 @@ __device__ __forceinline__ int drj_sync_or(bool warp_local, int pred) {
 // TEAM = one thread-block cluster per chain (few chains x long data, see drj_sweep_item_team): every
 // thread is a replica of rung (tid mod R) of the cluster's chain and runs the whole update redundantly;
 // `valid` = the thread holds a real particle, `active` = it is the replica that writes to HBM.
-template <class M, bool STREAM, bool TEAM>
+template <class M, bool STREAM, int MODE>
 __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
-  static_assert(!(STREAM && TEAM), "TEAM replicas keep their state in registers");
+  constexpr bool TEAM = MODE == DRJ_MODE_TEAM, GRID = MODE == DRJ_MODE_GRID;
+  static_assert(!(STREAM && MODE != DRJ_MODE_SOLO), "TEAM / GRID replicas keep their state in registers");
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
   const int R = a.rungs;
   const int tid = threadIdx.x;
   const int lc = tid / R, r = tid - lc * R;
-  const long long chain = TEAM ? (long long)drj_cluster_id_x() : (long long)blockIdx.x * a.chains_per_cta + lc;
-  const bool active = TEAM ? (lc == 0 && drj_cluster_ctarank() == 0u) : ((lc < a.chains_per_cta) && (chain < a.chains));
-  const bool valid = TEAM || active;
+  // GRID: every CTA holds all chains (thread tid < P = particle tid); CTA 0's replicas write to HBM
+  const long long chain = TEAM ? (long long)drj_cluster_id_x() : (GRID ? (long long)lc : (long long)blockIdx.x * a.chains_per_cta + lc);
+  const bool valid = TEAM || (GRID ? (chain < a.chains) : ((lc < a.chains_per_cta) && (chain < a.chains)));
+  const bool active = TEAM ? (lc == 0 && drj_cluster_ctarank() == 0u) : (valid && (!GRID || blockIdx.x == 0));
   const long long cc = valid ? chain : 0;
   const long long p = cc * R + r;
   const long long P = a.P;
@@ -767,7 +967,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   if (tid < DRJ_NT) s_mc[tid] = 0;  // (TEAM CTAs have more threads than DRJ_NT; only slot 0, tid < R, uses these arrays)
 
   DrjTiles<M> T;
-  T.template init<TEAM>(a);
+  T.template init<MODE>(a);
   __syncthreads();
 
   // ---- load state into registers
@@ -781,7 +981,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   const unsigned gchain_hi = (unsigned)((unsigned long long)(a.chain_offset + cc) >> 32);
   const unsigned k0 = (unsigned)a.seed, k1 = (unsigned)(a.seed >> 32);
   const bool do_couple = a.coupling_on && R > 1;
-  const bool wl = !TEAM && a.warp_local != 0;
+  const bool wl = MODE == DRJ_MODE_SOLO && a.warp_local != 0;
   const int lane = tid & 31;
 
   for (int it = 0; it < a.n_iter; ++it) {
@@ -815,7 +1015,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         case 2: th_p = exp(phi_p) + tmin; lo_p = log(th_p - tmin); adj = lo_p - s.alo[i]; break;
         default: {
           const double e = exp(phi_p);
-          th_p = (tmax * e + tmin) / (1.0 + e);
+          th_p = __dadd_rn(__dmul_rn(tmax, e), tmin) / (1.0 + e);  // (no FMA: the reference rounds the product, Particle.cpp:68)
           hi_p = log(tmax - th_p); lo_p = log(th_p - tmin);
           adj = hi_p + lo_p - s.ahi[i] - s.alo[i];
         } break;
@@ -835,7 +1035,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           drj_load_state<M>(a, s, p);
           s.llb_p[B == 1 ? 0 : b - 1] = fast ? M::finish(k, acc, n) : M::loglike(s.theta, a.data, a.misc, b);
         } else {
-          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, TEAM>(T, a, s.theta, b);
+          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, MODE>(T, a, s.theta, b, (int)p);
         }
       }
       double ll_p = 0.0;
@@ -849,9 +1049,11 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         if (err && active) drj_report(a, err, it, chain, r, i, p, s.theta, D);
       }
       // Metropolis-Hastings (Particle.h:131-139)
+      // (explicitly rounded product and sums, left to right as the reference's expression: an FMA contraction here
+      // could flip a decision that sits within an ulp of log u)
       double MH;
-      if (beta == 0.0) MH = (lp_p - s.lp) + adj;
-      else MH = beta * (ll_p - s.ll) + (lp_p - s.lp) + adj;
+      if (beta == 0.0) MH = __dadd_rn(lp_p - s.lp, adj);
+      else MH = __dadd_rn(__dadd_rn(__dmul_rn(beta, ll_p - s.ll), lp_p - s.lp), adj);
       const bool accept = (log(u3) < MH) && (err == 0);
       const double gain = rsqrt((double)s.bwi[i]);  // bw_stepsize = 1
       if (accept) {
@@ -913,8 +1115,9 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       const int wb = wl ? ((tid & ~31) + lane * R) : tid * R;
       const int wlc = wb / R;
       const bool walker = TEAM ? (tid == 0)
-                               : ((wl ? (lane < 32 / R) : true) && wlc < a.chains_per_cta &&
-                                  (long long)blockIdx.x * a.chains_per_cta + wlc < a.chains);
+                               : (GRID ? (tid < a.chains)
+                                       : ((wl ? (lane < 32 / R) : true) && wlc < a.chains_per_cta &&
+                                          (long long)blockIdx.x * a.chains_per_cta + wlc < a.chains));
       if (walker) {
         int cur_src = 0;
         double cur_ll = s_x[wb];
@@ -923,8 +1126,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           const double ll2 = s_x[wb + i + 1];
           const double b2 = s_beta[i + 1];
           double acceptance;
-          if (b1 == 0.0) acceptance = (cur_ll * b2) - (ll2 * b2);
-          else acceptance = (ll2 * b1 + cur_ll * b2) - (cur_ll * b1 + ll2 * b2);
+          // main.cpp:300-308, every product rounded (no FMA contraction in a decision)
+          if (b1 == 0.0) acceptance = __dsub_rn(__dmul_rn(cur_ll, b2), __dmul_rn(ll2, b2));
+          else acceptance = __dsub_rn(__dadd_rn(__dmul_rn(ll2, b1), __dmul_rn(cur_ll, b2)),
+                                      __dadd_rn(__dmul_rn(cur_ll, b1), __dmul_rn(ll2, b2)));
           if (s_logu[wb + i] < acceptance) {
             s_src[wb + i] = (short)(i + 1);  // rung i receives the replica that sat at rung i+1
             s_mc[wb + i]++;
@@ -938,7 +1143,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         s_src[wb + R - 1] = (short)cur_src;
       }
       drj_sync(wl);
-      const int src = TEAM ? (int)s_src[r] : (active ? (int)s_src[tid] : r);
+      const int src = TEAM ? (int)s_src[r] : (valid ? (int)s_src[tid] : r);
       const int from = base + src;
       if (drj_sync_or(wl, src != r)) {
         // replica-owned state moves: theta, phi, Jacobian logs, loglike_block, loglike, logprior.
@@ -984,10 +1189,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
     // ================= abort on error (Rcpp::stop in the reference) =================
     // one barrier: own error, or (seen by thread 0) an error reported by any other CTA
-    // (TEAM: the decision must be the same in every CTA of the cluster, which meet at a cluster barrier
-    // in the next sweep -- own error only, it is identical in all replicas)
+    // (TEAM / GRID: the decision must be the same in every CTA of the cluster / grid, which meet at a barrier
+    // in the next sweep -- own errors only, they are identical in all replicas)
     int stop = err;
-    if (!TEAM && (wl ? lane == 0 : tid == 0) && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
+    if (MODE == DRJ_MODE_SOLO && (wl ? lane == 0 : tid == 0) && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
     if (drj_sync_or(wl, stop)) break;
   }
   drj_sync(wl);
@@ -1002,7 +1207,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 // ------------------------------------------------------------------ kernels
 template <class M>
 __global__ void __launch_bounds__(DRJ_NT) drj_init_kernel(const __grid_constant__ DrjKernelArgs a) {
-  drj_init_body<M, false>(a);
+  drj_init_body<M, DRJ_MODE_SOLO>(a);
 }
 template <class M>
 __global__ void __launch_bounds__(DRJ_NT) drj_init_chain_kernel(const __grid_constant__ DrjKernelArgs a) {
@@ -1010,16 +1215,25 @@ __global__ void __launch_bounds__(DRJ_NT) drj_init_chain_kernel(const __grid_con
 }
 template <class M, bool STREAM>
 __global__ void __launch_bounds__(DRJ_NT, (STREAM ? 2 : DRJ_MINB)) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
-  drj_sweep_body<M, STREAM, false>(a);
+  drj_sweep_body<M, STREAM, DRJ_MODE_SOLO>(a);
 }
 // cluster-per-chain variants (launched with a cluster dimension of a.team_ctas; datum-form models only)
 template <class M>
 __global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_init_kernel_team(const __grid_constant__ DrjKernelArgs a) {
-  drj_init_body<M, true>(a);
+  drj_init_body<M, DRJ_MODE_TEAM>(a);
 }
 template <class M>
 __global__ void __launch_bounds__(DRJ_TEAM_NT, 1) drj_sweep_kernel_team(const __grid_constant__ DrjKernelArgs a) {
-  drj_sweep_body<M, false, true>(a);
+  drj_sweep_body<M, false, DRJ_MODE_TEAM>(a);
+}
+// grid-per-run variants (cooperative launch: all CTAs co-resident; datum-form models only)
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT, 1) drj_init_kernel_grid(const __grid_constant__ DrjKernelArgs a) {
+  drj_init_body<M, DRJ_MODE_GRID>(a);
+}
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT, 1) drj_sweep_kernel_grid(const __grid_constant__ DrjKernelArgs a) {
+  drj_sweep_body<M, false, DRJ_MODE_GRID>(a);
 }
 // addresses of the variants that only exist for datum-form models
 template <class M, bool DF = M::DATUM_FORM>
@@ -1027,10 +1241,14 @@ struct DrjStreamKernel {
   static const void* get() { return nullptr; }
   static const void* team_init() { return nullptr; }
   static const void* team_sweep() { return nullptr; }
+  static const void* grid_init() { return nullptr; }
+  static const void* grid_sweep() { return nullptr; }
 };
 template <class M>
 struct DrjStreamKernel<M, true> {
   static const void* get() { return (const void*)drj_sweep_kernel<M, true>; }
   static const void* team_init() { return (const void*)drj_init_kernel_team<M>; }
   static const void* team_sweep() { return (const void*)drj_sweep_kernel_team<M>; }
+  static const void* grid_init() { return (const void*)drj_init_kernel_grid<M>; }
+  static const void* grid_sweep() { return (const void*)drj_sweep_kernel_grid<M>; }
 };

@@ -100,6 +100,7 @@ class RunSpec:
     iters_per_launch: int = 0
     chains_per_cta: int = 0
     flags: int = 0
+    layout_chains: int = 0            # chains of the whole run when this spec is a shard of it (kernel family / reduction layout)
     data: Sequence = ()
     misc: Sequence = ()
     data_names: Sequence[str] | None = None
@@ -150,6 +151,7 @@ class RunSpec:
         c.seed, c.chain_offset = int(self.seed) & (2**64 - 1), int(self.chain_offset)
         c.replay_uniforms = L.dptr(self.replay) if self.rng_mode == "replay" else None
         c.iters_per_launch, c.chains_per_cta, c.flags = self.iters_per_launch, self.chains_per_cta, self.flags
+        c.layout_chains = int(self.layout_chains)
         return c
 
     def alloc_outputs(self, thin: int = 1, draws: bool = True) -> dict:
@@ -203,44 +205,88 @@ def run_raw(model: Model, spec: RunSpec, progress=None) -> dict:
     return out
 
 
-class Session:
-    """State resident in HBM between calls (drj_session_*)."""
+def _device_array(devices):
+    """None = all visible devices."""
+    if devices is None:
+        return None, 0
+    arr = (C.c_int32 * len(devices))(*[int(v) for v in devices])
+    return arr, len(devices)
 
-    def __init__(self, model: Model, spec: RunSpec):
+
+def run_raw_multi(model: Model, spec: RunSpec, devices=None, progress=None) -> dict:
+    """One call of drj_run_mcmc_multi: all chains of `spec` split over `devices` (None = every visible GPU) inside
+    the library, one host thread per device, outputs written straight into their chain slices."""
+    lib = L.lib()
+    dev0 = int(devices[0]) if devices else 0
+    h = model.handle(spec.d, spec.n_block, dev0, spec.param_names, spec.data_names, spec.misc_names)
+    cfg = spec.c_config()
+    dl, keep1 = L.make_list(spec.data, spec.data_names)
+    ml, keep2 = L.make_list(spec.misc, spec.misc_names)
+    out = spec.alloc_outputs()
+    cout = _c_output(out)
+    err = L.DrjError()
+    cb = L.PROGRESS_FN(progress) if progress is not None else L.PROGRESS_FN()
+    arr, n = _device_array(devices)
+    rc = lib.drj_run_mcmc_multi(C.byref(cfg), arr, n, h, C.byref(dl), C.byref(ml), C.byref(cout), cb, None, C.byref(err))
+    L.raise_for(rc, err, spec.d)
+    return out
+
+
+class Session:
+    """State resident in HBM between calls (drj_session_*); with `devices` (a list, or "all") the chains are
+    split over several GPUs inside the library (drj_multi_*): same methods, merged results."""
+
+    def __init__(self, model: Model, spec: RunSpec, devices=None):
         lib = L.lib()
         self.spec, self.model = spec, model
-        h = model.handle(spec.d, spec.n_block, spec.device, spec.param_names, spec.data_names, spec.misc_names)
+        self.multi = devices is not None
+        if devices == "all":
+            devices = None
+        dev0 = (int(devices[0]) if devices else 0) if self.multi else spec.device
+        h = model.handle(spec.d, spec.n_block, dev0, spec.param_names, spec.data_names, spec.misc_names)
         cfg = spec.c_config()
         dl, keep1 = L.make_list(spec.data, spec.data_names)
         ml, keep2 = L.make_list(spec.misc, spec.misc_names)
         self._h = C.c_void_p()
         err = L.DrjError()
-        rc = lib.drj_session_create(C.byref(cfg), h, C.byref(dl), C.byref(ml), C.byref(self._h), C.byref(err))
+        if self.multi:
+            arr, n = _device_array(devices)
+            rc = lib.drj_multi_create(C.byref(cfg), arr, n, h, C.byref(dl), C.byref(ml), C.byref(self._h), C.byref(err))
+        else:
+            rc = lib.drj_session_create(C.byref(cfg), h, C.byref(dl), C.byref(ml), C.byref(self._h), C.byref(err))
         L.raise_for(rc, err, spec.d)
 
+    def n_devices(self) -> int:
+        return int(L.lib().drj_multi_device_count(self._h)) if self.multi else 1
+
     def advance(self, n_iter: int) -> float:
-        """Advance n_iter updates; returns the CUDA-event time (ms) of the sweep kernels."""
+        """Advance n_iter updates; returns the CUDA-event time (ms) of the sweep kernels (max over the devices)."""
         ms = C.c_float(0)
         err = L.DrjError()
-        rc = L.lib().drj_session_advance(self._h, int(n_iter), C.byref(ms), C.byref(err))
+        fn = L.lib().drj_multi_advance if self.multi else L.lib().drj_session_advance
+        rc = fn(self._h, int(n_iter), C.byref(ms), C.byref(err))
         L.raise_for(rc, err, self.spec.d)
         return float(ms.value)
 
     def iterations_done(self) -> int:
+        if self.multi:
+            raise NotImplementedError("iterations_done() is a one-device query")
         return int(L.lib().drj_session_iterations_done(self._h))
 
     def launches(self) -> tuple[int, int]:
         a, b = C.c_int64(0), C.c_int64(0)
-        L.lib().drj_session_launches(self._h, C.byref(a), C.byref(b))
+        (L.lib().drj_multi_launches if self.multi else L.lib().drj_session_launches)(self._h, C.byref(a), C.byref(b))
         return int(a.value), int(b.value)
 
     def timing(self) -> tuple[float, float]:
         """Cumulative CUDA-event ms on the session stream: (sweep kernels, sweep kernels + transposes)."""
+        if self.multi:
+            raise NotImplementedError("timing() is a one-device query; advance() returns the max over the devices")
         a, b = C.c_double(0), C.c_double(0)
         L.lib().drj_session_timing(self._h, C.byref(a), C.byref(b))
         return float(a.value), float(b.value)
 
-    def summary(self, max_lag: int | None = None, center=None, moments: bool = True, autocov: bool = True) -> dict:
+    def summary(self, max_lag: int | None = None, center=None, moments: bool = True, autocov: bool = True, quantiles=None) -> dict:
         """On-device summaries of the cold-rung sampling draws (drj_session_summary): per-chain means and
         variances, autocovariance sums of the concatenated chains, deviance mean / variance.  Each part is a
         pass over the stored draws: `moments=False` / `autocov=False` skip the ones not needed (skipped parts
@@ -266,8 +312,13 @@ class Session:
                 raise ValueError("autocov without moments needs a center")
             sm.autocov_sum = L.dptr(out["autocov_sum"])
             sm.head, sm.tail = L.dptr(out["head"]), L.dptr(out["tail"])
+        probs = None
+        if quantiles is not None and len(quantiles):
+            probs = np.ascontiguousarray(quantiles, dtype=np.float64).ravel()
+            out["quantiles"] = np.zeros((sp.d, probs.size))
+            sm.n_quantiles, sm.quantile_probs, sm.quantiles = int(probs.size), L.dptr(probs), L.dptr(out["quantiles"])
         err = L.DrjError()
-        rc = L.lib().drj_session_summary(self._h, C.byref(sm), C.byref(err))
+        rc = (L.lib().drj_multi_summary if self.multi else L.lib().drj_session_summary)(self._h, C.byref(sm), C.byref(err))
         L.raise_for(rc, err, sp.d)
         out["max_lag"] = int(max_lag)
         return out
@@ -282,13 +333,14 @@ class Session:
         out = self.spec.alloc_outputs(thin if draws else 1, draws)
         cout = _c_output(out)
         err = L.DrjError()
-        rc = L.lib().drj_session_download_thinned(self._h, thin, C.byref(cout), C.byref(err))
+        fn = L.lib().drj_multi_download_thinned if self.multi else L.lib().drj_session_download_thinned
+        rc = fn(self._h, thin, C.byref(cout), C.byref(err))
         L.raise_for(rc, err, self.spec.d)
         return out
 
     def close(self):
         if self._h:
-            L.lib().drj_session_destroy(self._h)
+            (L.lib().drj_multi_destroy if self.multi else L.lib().drj_session_destroy)(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

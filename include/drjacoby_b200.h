@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DRJ_ABI_VERSION 1
+#define DRJ_ABI_VERSION 2
 
 /* status codes; 1..4 mirror the reference's Rcpp::stop() sites */
 enum {
@@ -89,7 +89,9 @@ typedef struct drj_config {
   int32_t iters_per_launch;  /* 0 = choose; iterations advanced by one kernel launch */
   int32_t chains_per_cta;    /* 0 = choose */
   int32_t flags;             /* DRJ_FLAG_* */
-  int32_t reserved;
+  int32_t layout_chains;     /* chains of the WHOLE run when this call is one shard of it (0 = `chains`): the kernel family
+                                and the reduction layout of the few-chains kernels are chosen from it, so that a shard
+                                reproduces its slice of the unsharded run bit for bit.  The multi-device entry points set it. */
 } drj_config;
 
 #define DRJ_FLAG_NO_TMA 1    /* stage data tiles with plain loads instead of the TMA bulk-copy engine */
@@ -97,6 +99,9 @@ typedef struct drj_config {
 #define DRJ_FLAG_RESIDENT_KERNEL 4 /* force the variant that keeps particle state in registers (default unless data is streamed) */
 #define DRJ_FLAG_TEAM_KERNEL 8      /* force the cluster-per-chain kernels (few chains x long data; datum-form models, rungs <= 64) */
 #define DRJ_FLAG_NO_TEAM_KERNEL 16  /* never use the cluster-per-chain kernels */
+#define DRJ_FLAG_GRID_KERNEL 32     /* force the grid-per-run kernels (chains x rungs <= 256 over data far larger than L2: every SM
+                                       streams 1/n_SM of the item once per sweep for all particles; datum-form models) */
+#define DRJ_FLAG_NO_GRID_KERNEL 64  /* never use the grid-per-run kernels */
 
 /* A model = the user's loglike + logprior (inst/templates/cpp_template.cpp:4-18).  Either a
  * built-in model (builtin != NULL) or CUDA source compiled at run time with NVRTC for sm_100a:
@@ -140,7 +145,7 @@ typedef struct drj_output {
  * concatenated chains, DIC from the deviance moments), without moving the draws to the host. */
 typedef struct drj_summary {
   int32_t max_lag;           /* in: autocovariance lags 0..max_lag (coda uses floor(10 log10 N)) */
-  int32_t reserved;
+  int32_t n_quantiles;       /* in: number of probabilities in quantile_probs (0 = none) */
   const double* center;      /* in: [d] centre of the autocovariance sums; NULL = mean over this call's chains */
   double* chain_mean;        /* out [chains][d]; may be NULL */
   double* chain_var;         /* out [chains][d] sample variance (n-1); may be NULL */
@@ -149,6 +154,10 @@ typedef struct drj_summary {
   double* head;              /* out [d][max_lag]: the first max_lag draws of the concatenated series; may be NULL */
   double* tail;              /* out [d][max_lag]: the last max_lag draws (with head: lets the caller add the lag
                                 products that straddle two shards when chains are split over GPUs); may be NULL */
+  const double* quantile_probs; /* in [n_quantiles], each in [0,1]; may be NULL */
+  double* quantiles;         /* out [d][n_quantiles]: R's quantile(x, probs) (type 7) of every parameter's cold-rung sampling
+                                draws, all chains together -- exact order statistics found by a radix select on the device
+                                (what summary() / the credible-interval plots compute from mcmc$output); may be NULL */
 } drj_summary;
 
 typedef struct drj_error {
@@ -206,6 +215,33 @@ int drj_session_launches(const drj_session* s, int64_t* sweep_launches, int64_t*
 /* cumulative CUDA-event time on the session's stream: sweep kernels only / sweep kernels + output transposes */
 int drj_session_timing(const drj_session* s, double* sweep_ms_total, double* stream_ms_total);
 void drj_session_destroy(drj_session* s);
+
+/* ---- one process, several GPUs: replaces the reference's only parallelism, the dispatch of chains over a PSOCK
+ * cluster (R/main.R:392-402: clusterApplyLB(cl = cluster, 1:chains, deploy_chain, ...)).  Chains are split into
+ * contiguous ranges, one per device; each device is driven by its own host thread (which never calls back into
+ * the caller: the progress hook runs on the calling thread only, as the R API requires, SURVEY 8b "Threading");
+ * every shard writes straight into its slice of the caller's chain-major buffers; the kernel family and the
+ * reduction layout are fixed from the whole run's size and the Philox counters carry global chain ids, so the
+ * result is bit for bit the one-device result.  devices == NULL or n_devices <= 0: all visible devices; devices
+ * beyond the number of chains stay idle; an ordinal listed twice gets two chain ranges, run side by side.
+ * cfg->device is ignored, cfg->chain_offset is added to every shard's offset. */
+typedef struct drj_multi drj_multi; /* opaque: one session per device */
+int drj_run_mcmc_multi(const drj_config* cfg, const int32_t* devices, int32_t n_devices, const drj_model* model,
+                       const drj_list* data, const drj_list* misc, drj_output* out, drj_progress_fn progress,
+                       void* progress_user, drj_error* err);
+int drj_multi_create(const drj_config* cfg, const int32_t* devices, int32_t n_devices, const drj_model* model,
+                     const drj_list* data, const drj_list* misc, drj_multi** out, drj_error* err);
+int drj_multi_device_count(const drj_multi* m); /* devices actually used */
+/* *kernel_ms (may be NULL): CUDA-event time of the sweep kernels of this call, max over the devices */
+int drj_multi_advance(drj_multi* m, int n_iter, float* kernel_ms, drj_error* err);
+int drj_multi_download_thinned(drj_multi* m, int thin, drj_output* out, drj_error* err); /* thin = 1: everything */
+/* drj_session_summary over ALL chains: per-chain moments from every device, the autocovariance sums about the
+ * global centre added over the devices plus the lag products that straddle two devices' chain ranges, pooled
+ * deviance moments, quantiles by a radix select whose histograms are added over the devices; merged on the host
+ * (a few KB per device).  head / tail refer to the whole concatenated series. */
+int drj_multi_summary(drj_multi* m, drj_summary* summary, drj_error* err);
+int drj_multi_launches(const drj_multi* m, int64_t* sweep_launches, int64_t* aux_launches); /* summed over devices */
+void drj_multi_destroy(drj_multi* m);
 
 /* ---- measurement helper: FP64 FMA throughput of `device` in TFLOP/s (2 flop per DFMA), the
  * roofline denominator for the compute-bound configs (MEASURED_PEAKS.json has no FP64 figure) */

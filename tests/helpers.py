@@ -92,11 +92,15 @@ def run_gpu(case: Case, rng_mode="replay", replay=None, seed=1, chain_offset=0, 
     return drj.run_raw(m, gpu_spec(case, rng_mode, replay, seed, chain_offset, **kw))
 
 
-def rel_close(a, b, rtol=1e-10, atol=1e-12):
+def rel_close(a, b, rtol=1e-10, atol=0.0):
+    """Pure relative gate (the north_star's "1e-10 relative"): |a - b| <= rtol |b|; equal infinities and exact zeros pass."""
     a, b = np.asarray(a), np.asarray(b)
     same_inf = (np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b)))
-    ok = same_inf | (np.abs(a - b) <= atol + rtol * np.abs(b))
-    return bool(ok.all()), float(np.nanmax(np.where(same_inf, 0.0, np.abs(a - b) / (atol / rtol + np.abs(b)))))
+    diff = np.where(same_inf, 0.0, np.abs(a - b))
+    ok = same_inf | (diff <= atol + rtol * np.abs(b))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(diff == 0.0, 0.0, diff / (atol / rtol + np.abs(b)))
+    return bool(ok.all()), float(np.nanmax(rel)) if rel.size else 0.0
 
 
 def assert_parity(gpu: dict, ora, rtol=1e-10, what=""):

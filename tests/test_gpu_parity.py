@@ -45,6 +45,10 @@ CASES = {
     "example_rungs256": Case("example", [-10, 0], [10, np.inf], data=[normal_data(8)], beta=beta_ladder(256), chains=2,
                              burnin=5, samples=5),
     "example_one_chain": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100)], chains=1, burnin=300, samples=300),
+    # BASELINE configs[0] at its full length: 1 chain, 1 rung, burnin 1e3 + samples 1e4, n = 100 (22,000 dependent updates)
+    "k1_full_length": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100, 1)], chains=1, burnin=1000, samples=10000),
+    "k1_full_length_exact": Case("example_exact", [-10, 0], [10, np.inf], data=[normal_data(100, 1)], chains=1, burnin=1000,
+                                 samples=10000),
     # empty data vector: the likelihood is an empty sum, the chain follows the prior
     "example_empty_data": Case("example", [-10, 0], [10, np.inf], data=[np.zeros(0)], beta=beta_ladder(2), chains=3),
     "example_exact_empty_data": Case("example_exact", [-10, 0], [10, np.inf], data=[np.zeros(0)], chains=2),

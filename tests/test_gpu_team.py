@@ -171,7 +171,7 @@ def test_team_full_size_data_against_sufficient_statistics():
     from test_gpu_fullsize import loglike_from_sufficient_stats
     x = np.random.Generator(np.random.Philox(1)).normal(3.0, 2.0, 10_000_000)
     case = Case("example", [-10, 0], [10, np.inf], data=[x], chains=5, burnin=30, samples=30)
-    out = run_gpu(case, "philox", seed=1)
+    out = run_gpu(case, "philox", seed=1, flags=flags().FLAG_TEAM_KERNEL)
     th = np.concatenate([out["theta_burnin"], out["theta_sampling"]], axis=2)
     ll = np.concatenate([out["loglike_burnin"], out["loglike_sampling"]], axis=2)
     want = loglike_from_sufficient_stats(x, th[..., 0], th[..., 1])

@@ -1,6 +1,6 @@
 """Host-side logic of the run_mcmc mirror (no GPU): argument checks, pre-processing, R-compatible
 stream generation, post-processing / diagnostics.  Where a sampler is needed the CPU oracle stands
-in for the CUDA engine through the api._SHARD_RUNNER hook (tests only; the product has no such path)."""
+in for the CUDA engine: the tests replace engine.run_raw (the product has no such seam)."""
 import json
 import os
 
@@ -31,7 +31,7 @@ def oracle_runner(po):
 
 @pytest.fixture()
 def cpu_engine(oracle, monkeypatch):
-    monkeypatch.setattr(api, "_SHARD_RUNNER", oracle_runner(oracle))
+    monkeypatch.setattr(api.engine, "run_raw", oracle_runner(oracle))
 
 
 # ---------------------------------------------------------------- define_params (R/main.R:48-139)
@@ -159,8 +159,15 @@ def test_output_object_schema(cpu_engine):
     assert res.parameters["df_params"]["trans_type"].tolist() == [3, 2]
     dev = -2 * out[out["phase"] == "sampling"]["loglikelihood"].to_numpy()
     assert np.isclose(res.diagnostics["DIC_Gelman"], dev.mean() + 0.5 * dev.var(ddof=1))
-    s = drj.sample_chains(res, 10)
-    assert list(s.columns) == ["sample", "mu", "sigma", "logprior", "loglikelihood"] and len(s) == 10
+    # R/samples.R:21-46: parameter columns only, `sample` appended last, rows seq.int(1, N, length.out = n) truncated
+    s = drj.sample_chains(res, 7)
+    assert list(s.columns) == ["mu", "sigma", "sample"] and len(s) == 7 and s["sample"].tolist() == list(range(1, 8))
+    samp = out[out["phase"] == "sampling"].reset_index(drop=True)
+    rows = np.floor(np.linspace(1, len(samp), 7)).astype(int) - 1   # 1, 10.83 -> 10, 20.67 -> 20, 30.5 -> 30, ... (R truncates)
+    assert rows.tolist() == [0, 9, 19, 29, 39, 49, 59]
+    assert np.array_equal(s["mu"].to_numpy(), samp["mu"].to_numpy()[rows])
+    sk = drj.sample_chains(res, 7, keep_chain_index=True)
+    assert list(sk.columns) == ["chain", "mu", "sigma", "sample"] and sk["chain"].tolist() == [1, 1, 1, 1, 2, 2, 2]
     with pytest.raises(ValueError):
         drj.sample_chains(res, 1000)
     # single rung: mc_accept is NA, no rhat for a single chain
@@ -213,7 +220,14 @@ def test_thinned_frame_numbering_and_shapes():
     assert o["loglike_sampling"].shape == (3, 2, 7) and o["accept_sampling"].shape == (3, 2)
     assert "theta_sampling" not in spec.alloc_outputs(draws=False)
     raw = {k: np.arange(v.size, dtype=float).reshape(v.shape) for k, v in o.items()}
-    f = api._thinned_frame(raw, ["a", "b"], 10, 25, 4, 3)
+    f, pt = api._thinned_frames(raw, ["a", "b"], 10, 25, 4, 3, 2, True)
+    # the `pt` frame of the reference (R/main.R:451-482): every stored rung, same thinned iterations, hot draws included
+    assert list(pt.columns) == ["chain", "rung", "phase", "iteration", "logprior", "loglikelihood", "a", "b"]
+    assert len(pt) == 3 * 2 * 10 and pt["rung"].tolist()[:20] == [1] * 10 + [2] * 10
+    hot = pt[(pt["chain"] == 2) & (pt["rung"] == 1)]
+    assert hot["iteration"].tolist() == [1, 5, 9, 11, 15, 19, 23, 27, 31, 35]
+    assert hot["loglikelihood"].tolist()[:3] == raw["loglike_burnin"][1, 0].tolist()
+    assert hot["b"].tolist()[3:] == raw["theta_sampling"][1, 0, :, 1].tolist()
     one = f[f["chain"] == 2]
     assert one["iteration"].tolist() == [1, 5, 9, 11, 15, 19, 23, 27, 31, 35]
     assert one["phase"].tolist() == ["burnin"] * 3 + ["sampling"] * 7
