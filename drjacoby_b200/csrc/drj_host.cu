@@ -1054,9 +1054,34 @@ static int solo_configure(drj_session* s, drj_error* err) {
 }
 
 // GRID kernels: opt in to the dynamic shared memory of the chunk pipeline; grid = every CTA the device can hold at once
-static int grid_configure(drj_session* s, drj_error* err) {
+static int grid_configure(drj_session* s, int& grid_stages, drj_error* err) {
   const drj_model* m = s->model;
   int per_sm = 0;
+  {  // as many 64 KB stages as fit next to the kernels' static shared memory (a user model's Consts table is part of it)
+    int stat = 0, optin = 0;
+    if (m->jit) {
+      int a = 0, b = 0;
+      CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuFuncGetAttribute", (void**)&FuncGetAttribute, cudaEnableDefault, &q) == cudaSuccess && FuncGetAttribute) {
+        FuncGetAttribute(&a, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, s->jf->grid_sweep_cu);
+        FuncGetAttribute(&b, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, s->jf->grid_init_cu);
+      }
+      stat = std::max(a, b);
+    } else {
+      cudaFuncAttributes fa;
+      CUDA_TRY(cudaFuncGetAttributes(&fa, m->grid_sweep_fn));
+      stat = (int)fa.sharedSizeBytes;
+      CUDA_TRY(cudaFuncGetAttributes(&fa, m->grid_init_fn));
+      stat = std::max(stat, (int)fa.sharedSizeBytes);
+    }
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->cfg.device);
+    const long long chunk_bytes = (long long)DRJ_GRID_CHUNK * sizeof(double);
+    const int fit = (int)(((long long)optin - stat - 1024 - 64) / chunk_bytes);
+    if (fit < 2) return set_err(err, DRJ_ERR_CUDA, "the grid kernels need two %lld-byte stages next to %d bytes of static shared memory", chunk_bytes, stat);
+    grid_stages = std::min(grid_stages, fit);
+    s->dyn_smem = (unsigned)(((long long)grid_stages * DRJ_GRID_CHUNK + 8) * sizeof(double));
+  }
   if (m->jit) {
     for (CUfunction f : {s->jf->grid_init_cu, s->jf->grid_sweep_cu})
       if (g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
@@ -1332,7 +1357,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   const long long layout_C = cfg->layout_chains > 0 ? std::max(cfg->layout_chains, C) : C;
   const long long layout_P = layout_C * R;
   int team_stages = 3;  // x 64 KB tiles
-  int grid_stages = 6;  // x 16 KB chunks
+  int grid_stages = 3;  // x 64 KB chunks (fewer if the model's static shared memory leaves less room: grid_configure)
   {
     long long longest = 0;
     if (data) for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
@@ -1396,7 +1421,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
       s->grid = C * s->team_ctas;
     } else if (s->gridk) {
       s->dyn_smem = (unsigned)(((long long)grid_stages * DRJ_GRID_CHUNK + 8) * sizeof(double));
-      int rc = grid_configure(s, err);
+      int rc = grid_configure(s, grid_stages, err);
       if (rc) return rc;
     } else {
       int rc = solo_configure(s, err);

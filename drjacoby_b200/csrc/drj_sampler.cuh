@@ -213,7 +213,10 @@ __device__ __forceinline__ double* drj_tile_buf() {
 // GRID kernels (few particles x data far larger than L2: the HBM-bound regime)
 #define DRJ_GRID_VRANKS 1184   // canonical number of partial sums a data item is split into: 8 per SM of a 148-SM B200
 #ifndef DRJ_GRID_CHUNK
-#define DRJ_GRID_CHUNK 2048    // doubles per TMA chunk (16 KB)
+#define DRJ_GRID_CHUNK 8192    // doubles per TMA chunk (64 KB).  Measured at n = 1e8 (profiles/README.md, round 2): the consumer side
+                               // pays ~800 cycles per chunk whatever its size (full/empty hand-shake, LDS latency at loop entry with
+                               // 2 warps per scheduler), so 16 KB chunks ran at 0.69 (1 x 1) / 0.44 (5 x 1) of the HBM peak, 64 KB
+                               // chunks at 0.98 / 0.80; the number of stages made no difference
 #endif
 #define DRJ_GRID_MAXSTAGES 12  // at most this many chunks in flight per CTA
 #define DRJ_GRID_MAXP 256      // at most this many particles (chains x rungs): every CTA holds a replica of each

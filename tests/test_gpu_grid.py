@@ -31,7 +31,7 @@ def F():
 
 
 GRID_CASES = {
-    # one particle, 35 chunks: 256 slots for the single particle
+    # one particle, 9 chunks of 8192 (ragged last one): 256 slots for the single particle
     "one_chain": Case("example", [-10, 0], [10, np.inf], data=[normal_data(70001)], chains=1, burnin=20, samples=20),
     # odd length, ragged last chunk, 3 chains x 2 rungs: 42 slots, 4 idle threads
     "stream_r2": Case("example", [-10, 0], [10, np.inf], data=[normal_data(10001)], beta=beta_ladder(2), chains=3,
@@ -44,8 +44,8 @@ GRID_CASES = {
     # the most particles a CTA can replicate: 8 x 32 = 256, one slot each
     "full_cta": Case("example", [-10, 0], [10, np.inf], data=[normal_data(5000)], beta=beta_ladder(32), chains=8,
                      burnin=5, samples=5),
-    # more chunks (1465) than virtual ranks (1184): ranks of one and two chunks
-    "many_chunks": Case("normal_mu", [-np.inf], [np.inf], data=[normal_data(3_000_001)], chains=2, burnin=4, samples=4),
+    # more chunks (1221) than virtual ranks (1184): ranks of one and two chunks
+    "many_chunks": Case("normal_mu", [-np.inf], [np.inf], data=[normal_data(10_000_001)], chains=2, burnin=3, samples=3),
 }
 
 
@@ -133,7 +133,7 @@ def test_grid_launch_split_and_sharding_are_bitwise_invariant():
 
 def test_grid_small_and_empty_data(oracle):
     """Forced onto data shorter than a chunk, and onto an empty vector: CTAs without chunks only meet at the barrier."""
-    for n in (0, 1, 7, 100, 2049):
+    for n in (0, 1, 7, 100, 8193):
         case = Case("example", [-10, 0], [10, np.inf], data=[normal_data(n)], beta=beta_ladder(2), chains=2, burnin=8,
                     samples=8)
         u = case.replay()
