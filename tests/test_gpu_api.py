@@ -476,7 +476,9 @@ def test_summary_mode_with_thinned_draws():
               seed=8, silent=True)
     full = drj.run_mcmc(**kw)
     thin = drj.run_mcmc(output="summary", thin=10, **kw)
-    assert thin.pt is None and thin.diagnostics["rhat"]["mu"] == full.diagnostics["rhat"]["mu"]
+    assert thin.diagnostics["rhat"]["mu"] == full.diagnostics["rhat"]["mu"]
+    keep_pt = full.pt[((full.pt["iteration"] - 1) % 10 == 0)].reset_index(drop=True)   # the pt frame (all rungs), same thinning
+    pd.testing.assert_frame_equal(thin.pt, keep_pt)
     assert abs(thin.diagnostics["ess"]["sigma"] - full.diagnostics["ess"]["sigma"]) <= 1e-8 * full.diagnostics["ess"]["sigma"]
     keep = full.output[((full.output["iteration"] - 1) % 10 == 0)].reset_index(drop=True)
     assert len(thin.output) == 4 * (10 + 100) and list(thin.output.columns) == list(full.output.columns)
