@@ -66,21 +66,24 @@ __device__ __forceinline__ double drj_u32_to_unif(unsigned int w) {
 }
 
 // ----------------------------------------------------------------------------- qnorm (AS241)
+// Both rational approximations (central |q| <= 0.425, tail r = sqrt(-log(min(p, 1-p))) <= 5) are evaluated for every
+// draw and the result selected: 15 % of the draws are tail draws, so a warp of 32 practically always needs both
+// anyway, and as a branch the two sides ran one after the other with part of the lanes idle.  Only the far tail
+// (r > 5: p < 1.4e-11) stays a branch.  Same expressions as AS241 / R's qnorm, hence the same bits as before.
 __device__ __forceinline__ double drj_qnorm(double p) {
-  double q = p - 0.5, r, val;
-  if (fabs(q) <= 0.425) {
-    r = 0.180625 - q * q;
-    val = q *
-          (((((((r * 2509.0809287301226727 + 33430.575583588128105) * r + 67265.770927008700853) * r +
-               45921.953931549871457) * r + 13731.693765509461125) * r + 1971.5909503065514427) * r +
-            133.14166789178437745) * r + 3.387132872796366608) /
-          (((((((r * 5226.495278852545925 + 28729.085735721942674) * r + 39307.89580009271061) * r +
-               21213.794301586595867) * r + 5394.1960214247511077) * r + 687.1870074920579083) * r +
-            42.313330701600911252) * r + 1.0);
-    return val;
-  }
-  r = (q < 0.0) ? p : (1.0 - p);
+  const double q = p - 0.5;
+  const double rc = 0.180625 - q * q;
+  const double val_c =
+      q *
+      (((((((rc * 2509.0809287301226727 + 33430.575583588128105) * rc + 67265.770927008700853) * rc +
+           45921.953931549871457) * rc + 13731.693765509461125) * rc + 1971.5909503065514427) * rc +
+        133.14166789178437745) * rc + 3.387132872796366608) /
+      (((((((rc * 5226.495278852545925 + 28729.085735721942674) * rc + 39307.89580009271061) * rc +
+           21213.794301586595867) * rc + 5394.1960214247511077) * rc + 687.1870074920579083) * rc +
+        42.313330701600911252) * rc + 1.0);
+  double r = (q < 0.0) ? p : (1.0 - p);
   r = sqrt(-log(r));
+  double val;
   if (r <= 5.0) {
     r -= 1.6;
     val = (((((((r * 7.7454501427834140764e-4 + 0.0227238449892691845833) * r +
@@ -98,7 +101,8 @@ __device__ __forceinline__ double drj_qnorm(double p) {
                 1.8463183175100546818e-5) * r + 7.868691311456132591e-4) * r + 0.0148753612908506148525) * r +
              0.13692988092273580531) * r + 0.59983220655588793769) * r + 1.0);
   }
-  return (q < 0.0) ? -val : val;
+  val = (q < 0.0) ? -val : val;
+  return (fabs(q) <= 0.425) ? val_c : val;
 }
 
 // R::rnorm(mu, sigma) by inversion from two 32-bit-resolution uniforms (norm_rand, INVERSION)

@@ -1429,6 +1429,12 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     }
   }
 
+  if (const char* e = getenv("DRJ_CARVEOUT")) {  // tuning: shared-memory carve-out (percent) of the one-thread-per-particle sweep kernel
+    const int pct = atoi(e);
+    if (!s->team && !s->gridk && !model->jit && pct >= 0 && pct <= 100)
+      cudaFuncSetAttribute(s->stream_variant ? model->stream_fn : model->sweep_fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
+
   // ---- uploads
   DrjKernelArgs& a = s->a;
   memset(&a, 0, sizeof(a));

@@ -958,8 +958,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   __shared__ int s_trans[D], s_free[D];
   __shared__ double s_x[DRJ_EXCH * DRJ_NT];  // rung-swap exchange buffer; s_x[0..NT) doubles as loglike
   __shared__ double s_logu[DRJ_NT];
-  __shared__ short s_src[DRJ_NT];
-  __shared__ int s_mc[DRJ_NT];
+  __shared__ unsigned s_swap[DRJ_NT / 2];  // swap outcome of every pair, one bit each, (R + 30) / 32 words per chain
   __shared__ double s_beta[DRJ_NT];
 
   for (int i = tid; i < R; i += blockDim.x) s_beta[i] = a.beta_raised[i];
@@ -967,7 +966,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
     s_tmin[i] = a.theta_min[i]; s_tmax[i] = a.theta_max[i];
     s_trans[i] = a.trans_type[i]; s_free[i] = a.free_slot[i];
   }
-  if (tid < DRJ_NT) s_mc[tid] = 0;  // (TEAM CTAs have more threads than DRJ_NT; only slot 0, tid < R, uses these arrays)
+  int mc_count = 0;  // swaps accepted at this rung's pair in this launch
 
   DrjTiles<M> T;
   T.template init<MODE>(a);
@@ -1059,23 +1058,23 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       else MH = __dadd_rn(__dadd_rn(__dmul_rn(beta, ll_p - s.ll), lp_p - s.lp), adj);
       const bool accept = (log(u3) < MH) && (err == 0);
       const double gain = rsqrt((double)s.bwi[i]);  // bw_stepsize = 1
-      if (accept) {
-        s.phi[i] = phi_p; s.alo[i] = lo_p; s.ahi[i] = hi_p;
-        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
-          const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
-          s.llb[b] = s.llb_p[b];
-        }
-        s.ll = ll_p; s.lp = lp_p;
-        s.logbw[i] += (1.0 - target) * gain;  // Robbins-Monro, log scale (Particle.h:153)
-        s.acc++;
-      } else {
-        s.theta[i] = th_cur;
-        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
-          const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
-          s.llb_p[b] = s.llb[b];
-        }
-        s.logbw[i] -= target * gain;  // Particle.h:165
+      // accept / reject as selects, not as a branch: the lanes of a warp decide differently at every update, and a
+      // divergent branch here made every warp run both sides (n = 100 sweep: 26.7 of 32 lanes active, round 1)
+      s.phi[i] = accept ? phi_p : s.phi[i];
+      s.alo[i] = accept ? lo_p : s.alo[i];
+      s.ahi[i] = accept ? hi_p : s.ahi[i];
+      s.theta[i] = accept ? th_p : th_cur;
+      for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+        const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
+        const double v = accept ? s.llb_p[b] : s.llb[b];
+        s.llb[b] = v;
+        s.llb_p[b] = v;
       }
+      s.ll = accept ? ll_p : s.ll;
+      s.lp = accept ? lp_p : s.lp;
+      // Robbins-Monro on the log scale: + (1 - a*) / sqrt(index) on acceptance (Particle.h:153), - a* / sqrt(index) otherwise (:165)
+      s.logbw[i] = fma(accept ? (1.0 - target) : -target, gain, s.logbw[i]);
+      s.acc += accept ? 1 : 0;
       s.bwi[i]++;
     }
 
@@ -1099,7 +1098,16 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
     // ================= Metropolis coupling (main.cpp:282-344) =================
     if (do_couple) {
-      if (!TEAM || tid < R) s_x[tid] = s.ll;
+      // parallel part: every rung publishes its loglike, the two products of the pair BELOW it that do not depend on
+      // the outcome of earlier swaps (loglike2 * beta1, loglike2 * beta2: rung i+1 is untouched until pair i is
+      // decided), and the pair's log u
+      if (!TEAM || tid < R) {
+        s_x[tid] = s.ll;
+        if (r > 0) {
+          s_x[DRJ_NT + tid] = __dmul_rn(s.ll, s_beta[r - 1]);
+          s_x[2 * DRJ_NT + tid] = __dmul_rn(s.ll, beta);
+        }
+      }
       if (r < R - 1 && (!TEAM || tid < R)) {
         double u;
         if (a.rng_mode) u = rp[3LL * a.d_free * R + r];
@@ -1110,11 +1118,13 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         s_logu[tid] = log(u);
       }
       drj_sync(wl);
-      // sequential pass hot -> cold, one chain per LANE of the first warp(s) (not one lane of every
-      // warp: the walk is ~20 instructions x (R-1) steps at 1/32 lane efficiency, and with one walker
-      // per warp it was 18 % of all issued instructions of the n = 100 sweep, profiles/README.md).
+      // sequential part hot -> cold (the swap of pair i sees the outcome of pair i-1: the replica that moves up carries
+      // its loglike), one chain per LANE of the first warp(s).  The walker only DECIDES: per pair two products with the
+      // carried loglike, three rounded sums, a compare; the outcome is one bit of a mask.  (Round 1 wrote the source
+      // rung and the swap count of every pair from inside this loop: ~70 instructions per pair at 4/32 lanes, 17 % of
+      // all instructions issued by the n = 100 sweep with 32 rungs, and the other warps of the CTA waiting for it.)
       // warp_local: the first 32/R lanes of each warp walk that warp's chains.
-      // The replica that is swapped upwards is carried along.
+      const int W = (R + 30) >> 5;  // mask words per chain (R - 1 pairs)
       const int wb = wl ? ((tid & ~31) + lane * R) : tid * R;
       const int wlc = wb / R;
       const bool walker = TEAM ? (tid == 0)
@@ -1122,31 +1132,38 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
                                        : ((wl ? (lane < 32 / R) : true) && wlc < a.chains_per_cta &&
                                           (long long)blockIdx.x * a.chains_per_cta + wlc < a.chains));
       if (walker) {
-        int cur_src = 0;
+        unsigned m = 0u;
         double cur_ll = s_x[wb];
         double b1 = s_beta[0];
+#pragma unroll 4
         for (int i = 0; i < R - 1; ++i) {
-          const double ll2 = s_x[wb + i + 1];
-          const double b2 = s_beta[i + 1];
-          double acceptance;
-          // main.cpp:300-308, every product rounded (no FMA contraction in a decision)
-          if (b1 == 0.0) acceptance = __dsub_rn(__dmul_rn(cur_ll, b2), __dmul_rn(ll2, b2));
-          else acceptance = __dsub_rn(__dadd_rn(__dmul_rn(ll2, b1), __dmul_rn(cur_ll, b2)),
-                                      __dadd_rn(__dmul_rn(cur_ll, b1), __dmul_rn(ll2, b2)));
-          if (s_logu[wb + i] < acceptance) {
-            s_src[wb + i] = (short)(i + 1);  // rung i receives the replica that sat at rung i+1
-            s_mc[wb + i]++;
-          } else {
-            s_src[wb + i] = (short)cur_src;
-            cur_src = i + 1;
-            cur_ll = ll2;
-          }
+          const double ll2 = s_x[wb + i + 1], q1 = s_x[DRJ_NT + wb + i + 1], q2 = s_x[2 * DRJ_NT + wb + i + 1];
+          const double b2 = s_beta[i + 1], lu = s_logu[wb + i];
+          // main.cpp:300-308, every product and sum rounded (no FMA contraction in a decision):
+          //   (loglike2 * beta1 + loglike1 * beta2) - (loglike1 * beta1 + loglike2 * beta2)
+          const double t1 = __dmul_rn(cur_ll, b2), t2 = __dmul_rn(cur_ll, b1);
+          const double acceptance = (b1 == 0.0) ? __dsub_rn(t1, q2) : __dsub_rn(__dadd_rn(q1, t1), __dadd_rn(t2, q2));
+          const bool swap = lu < acceptance;
+          m |= (swap ? 1u : 0u) << (i & 31);
+          cur_ll = swap ? cur_ll : ll2;  // rejected: the replica of rung i+1 becomes the one that may move up
           b1 = b2;
+          if ((i & 31) == 31) { s_swap[wlc * W + (i >> 5)] = m; m = 0u; }
         }
-        s_src[wb + R - 1] = (short)cur_src;
+        if ((R - 1) & 31) s_swap[wlc * W + ((R - 2) >> 5)] = m;
       }
       drj_sync(wl);
-      const int src = TEAM ? (int)s_src[r] : (valid ? (int)s_src[tid] : r);
+      // parallel part: rung r receives the replica of rung r+1 if pair r swapped, else the replica that was being
+      // carried up: the one from below the run of swapped pairs that ends at pair r-1
+      int src = r;
+      if (valid) {
+        const unsigned* sw = s_swap + (TEAM ? 0 : lc) * W;
+        if (r < R - 1 && ((sw[r >> 5] >> (r & 31)) & 1u)) {
+          src = r + 1;
+          ++mc_count;
+        } else {
+          while (src > 0 && ((sw[(src - 1) >> 5] >> ((src - 1) & 31)) & 1u)) --src;
+        }
+      }
       const int from = base + src;
       if (drj_sync_or(wl, src != r)) {
         // replica-owned state moves: theta, phi, Jacobian logs, loglike_block, loglike, logprior.
@@ -1203,7 +1220,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   // ---- write state back
   if (active) {
     drj_store_state<M>(a, s, p);
-    if (do_couple && r < R - 1) a.mc_accept[chain * (R - 1) + r] += s_mc[tid];
+    if (do_couple && r < R - 1) a.mc_accept[chain * (R - 1) + r] += mc_count;
   }
 }
 
