@@ -104,6 +104,43 @@ __device__ __forceinline__ double drj_qnorm(double p) {
   val = (q < 0.0) ? -val : val;
   return (fabs(q) <= 0.425) ? val_c : val;
 }
+#ifdef DRJ_QNORM_BRANCHY
+__device__ __forceinline__ double drj_qnorm_branchy(double p) {
+  double q = p - 0.5, r, val;
+  if (fabs(q) <= 0.425) {
+    r = 0.180625 - q * q;
+    val = q *
+          (((((((r * 2509.0809287301226727 + 33430.575583588128105) * r + 67265.770927008700853) * r +
+               45921.953931549871457) * r + 13731.693765509461125) * r + 1971.5909503065514427) * r +
+            133.14166789178437745) * r + 3.387132872796366608) /
+          (((((((r * 5226.495278852545925 + 28729.085735721942674) * r + 39307.89580009271061) * r +
+               21213.794301586595867) * r + 5394.1960214247511077) * r + 687.1870074920579083) * r +
+            42.313330701600911252) * r + 1.0);
+    return val;
+  }
+  r = (q < 0.0) ? p : (1.0 - p);
+  r = sqrt(-log(r));
+  if (r <= 5.0) {
+    r -= 1.6;
+    val = (((((((r * 7.7454501427834140764e-4 + 0.0227238449892691845833) * r +
+                0.24178072517745061177) * r + 1.27045825245236838258) * r + 3.64784832476320460504) * r +
+             5.7694972214606914055) * r + 4.6303378461565452959) * r + 1.42343711074968357734) /
+          (((((((r * 1.05075007164441684324e-9 + 5.475938084995344946e-4) * r +
+                0.0151986665636164571966) * r + 0.14810397642748007459) * r + 0.68976733498510000455) * r +
+             1.6763848301838038494) * r + 2.05319162663775882187) * r + 1.0);
+  } else {
+    r -= 5.0;
+    val = (((((((r * 2.01033439929228813265e-7 + 2.71155556874348757815e-5) * r +
+                0.0012426609473880784386) * r + 0.026532189526576123093) * r + 0.29656057182850489123) * r +
+             1.7848265399172913358) * r + 5.4637849111641143699) * r + 6.6579046435011037772) /
+          (((((((r * 2.04426310338993978564e-15 + 1.4215117583164458887e-7) * r +
+                1.8463183175100546818e-5) * r + 7.868691311456132591e-4) * r + 0.0148753612908506148525) * r +
+             0.13692988092273580531) * r + 0.59983220655588793769) * r + 1.0);
+  }
+  return (q < 0.0) ? -val : val;
+}
+#define drj_qnorm drj_qnorm_branchy
+#endif
 
 // R::rnorm(mu, sigma) by inversion from two 32-bit-resolution uniforms (norm_rand, INVERSION)
 __device__ __forceinline__ double drj_rnorm(double mu, double sigma, double u1, double u2) {

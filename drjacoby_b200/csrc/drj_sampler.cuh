@@ -1060,6 +1060,26 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       const double gain = rsqrt((double)s.bwi[i]);  // bw_stepsize = 1
       // accept / reject as selects, not as a branch: the lanes of a warp decide differently at every update, and a
       // divergent branch here made every warp run both sides (n = 100 sweep: 26.7 of 32 lanes active, round 1)
+#ifdef DRJ_ACCEPT_BRANCH
+      if (accept) {
+        s.phi[i] = phi_p; s.alo[i] = lo_p; s.ahi[i] = hi_p;
+        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+          const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
+          s.llb[b] = s.llb_p[b];
+        }
+        s.ll = ll_p; s.lp = lp_p;
+        s.logbw[i] = fma(1.0 - target, gain, s.logbw[i]);
+        s.acc++;
+      } else {
+        s.theta[i] = th_cur;
+        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+          const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
+          s.llb_p[b] = s.llb[b];
+        }
+        s.logbw[i] = fma(-target, gain, s.logbw[i]);
+      }
+      s.bwi[i]++;
+#else
       s.phi[i] = accept ? phi_p : s.phi[i];
       s.alo[i] = accept ? lo_p : s.alo[i];
       s.ahi[i] = accept ? hi_p : s.ahi[i];
@@ -1076,6 +1096,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       s.logbw[i] = fma(accept ? (1.0 - target) : -target, gain, s.logbw[i]);
       s.acc += accept ? 1 : 0;
       s.bwi[i]++;
+#endif
     }
 
     // ================= store (before coupling, main.cpp:165-173) =================
@@ -1161,7 +1182,15 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           src = r + 1;
           ++mc_count;
         } else {
-          while (src > 0 && ((sw[(src - 1) >> 5] >> ((src - 1) & 31)) & 1u)) --src;
+          // highest pair below r that did NOT swap, + 1 (0 if every pair below swapped): one __clz per mask word, not a
+          // walk down the run -- on a ladder whose hot rungs swap almost always the runs are as long as the ladder
+          src = 0;
+          for (int pos = r; pos > 0;) {
+            const int w = (pos - 1) >> 5, nb = pos - (w << 5);  // bits [0, nb) of word w lie below `pos`
+            const unsigned zeros = ~sw[w] & (nb == 32 ? 0xffffffffu : ((1u << nb) - 1u));
+            if (zeros) { src = (w << 5) + 32 - __clz(zeros); break; }
+            pos = w << 5;
+          }
         }
       }
       const int from = base + src;
