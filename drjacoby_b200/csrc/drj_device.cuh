@@ -66,46 +66,10 @@ __device__ __forceinline__ double drj_u32_to_unif(unsigned int w) {
 }
 
 // ----------------------------------------------------------------------------- qnorm (AS241)
-// Both rational approximations (central |q| <= 0.425, tail r = sqrt(-log(min(p, 1-p))) <= 5) are evaluated for every
-// draw and the result selected: 15 % of the draws are tail draws, so a warp of 32 practically always needs both
-// anyway, and as a branch the two sides ran one after the other with part of the lanes idle.  Only the far tail
-// (r > 5: p < 1.4e-11) stays a branch.  Same expressions as AS241 / R's qnorm, hence the same bits as before.
+// (A branch-free variant -- both rationals evaluated for every draw, result selected -- was measured in round 2: no gain
+// on the throughput shapes (a warp of 32 draws nearly always needs the tail branch too: n = 100 sweep 1.05e10 either
+// way), and 8 % slower on a single chain, whose dependent chain then always contains the tail's log and sqrt.)
 __device__ __forceinline__ double drj_qnorm(double p) {
-  const double q = p - 0.5;
-  const double rc = 0.180625 - q * q;
-  const double val_c =
-      q *
-      (((((((rc * 2509.0809287301226727 + 33430.575583588128105) * rc + 67265.770927008700853) * rc +
-           45921.953931549871457) * rc + 13731.693765509461125) * rc + 1971.5909503065514427) * rc +
-        133.14166789178437745) * rc + 3.387132872796366608) /
-      (((((((rc * 5226.495278852545925 + 28729.085735721942674) * rc + 39307.89580009271061) * rc +
-           21213.794301586595867) * rc + 5394.1960214247511077) * rc + 687.1870074920579083) * rc +
-        42.313330701600911252) * rc + 1.0);
-  double r = (q < 0.0) ? p : (1.0 - p);
-  r = sqrt(-log(r));
-  double val;
-  if (r <= 5.0) {
-    r -= 1.6;
-    val = (((((((r * 7.7454501427834140764e-4 + 0.0227238449892691845833) * r +
-                0.24178072517745061177) * r + 1.27045825245236838258) * r + 3.64784832476320460504) * r +
-             5.7694972214606914055) * r + 4.6303378461565452959) * r + 1.42343711074968357734) /
-          (((((((r * 1.05075007164441684324e-9 + 5.475938084995344946e-4) * r +
-                0.0151986665636164571966) * r + 0.14810397642748007459) * r + 0.68976733498510000455) * r +
-             1.6763848301838038494) * r + 2.05319162663775882187) * r + 1.0);
-  } else {
-    r -= 5.0;
-    val = (((((((r * 2.01033439929228813265e-7 + 2.71155556874348757815e-5) * r +
-                0.0012426609473880784386) * r + 0.026532189526576123093) * r + 0.29656057182850489123) * r +
-             1.7848265399172913358) * r + 5.4637849111641143699) * r + 6.6579046435011037772) /
-          (((((((r * 2.04426310338993978564e-15 + 1.4215117583164458887e-7) * r +
-                1.8463183175100546818e-5) * r + 7.868691311456132591e-4) * r + 0.0148753612908506148525) * r +
-             0.13692988092273580531) * r + 0.59983220655588793769) * r + 1.0);
-  }
-  val = (q < 0.0) ? -val : val;
-  return (fabs(q) <= 0.425) ? val_c : val;
-}
-#ifdef DRJ_QNORM_BRANCHY
-__device__ __forceinline__ double drj_qnorm_branchy(double p) {
   double q = p - 0.5, r, val;
   if (fabs(q) <= 0.425) {
     r = 0.180625 - q * q;
@@ -139,8 +103,7 @@ __device__ __forceinline__ double drj_qnorm_branchy(double p) {
   }
   return (q < 0.0) ? -val : val;
 }
-#define drj_qnorm drj_qnorm_branchy
-#endif
+
 
 // R::rnorm(mu, sigma) by inversion from two 32-bit-resolution uniforms (norm_rand, INVERSION)
 __device__ __forceinline__ double drj_rnorm(double mu, double sigma, double u1, double u2) {
