@@ -23,6 +23,8 @@ RNG_PHILOX, RNG_REPLAY = 0, 1
 FLAG_NO_TMA, FLAG_STREAM_KERNEL, FLAG_RESIDENT_KERNEL = 1, 2, 4
 FLAG_TEAM_KERNEL, FLAG_NO_TEAM_KERNEL = 8, 16
 FLAG_GRID_KERNEL, FLAG_NO_GRID_KERNEL = 32, 64
+FLAG_LANES_KERNEL, FLAG_NO_LANES_KERNEL = 128, 256
+FLAG_SPEC_KERNEL, FLAG_NO_SPEC_KERNEL = 512, 1024
 
 
 class DrjList(C.Structure):

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libdrjacoby_b200.so")
 HEADERS = {"drj_device.cuh": "drj_embedded_device.inc", "drj_sampler.cuh": "drj_embedded_sampler.inc",
-           "drj_models.cuh": "drj_embedded_models.inc"}
+           "drj_models.cuh": "drj_embedded_models.inc", "drj_lanes.cuh": "drj_embedded_lanes.inc",
+           "drj_spec.cuh": "drj_embedded_spec.inc"}
 SOURCES = ["drj_host.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -105,13 +105,23 @@ __device__ __forceinline__ double drj_qnorm(double p) {
 }
 
 
-// R::rnorm(mu, sigma) by inversion from two 32-bit-resolution uniforms (norm_rand, INVERSION)
+// R::rnorm(mu, sigma) by inversion from two 32-bit-resolution uniforms (norm_rand, INVERSION), in two steps: the
+// standard normal draw (independent of the chain's state: the LANES kernels compute it ahead, one draw per lane) and
+// the location-scale step with R's argument checks
+__device__ __forceinline__ double drj_norm_rand(double u1, double u2) {
+  const double BIG = 134217728.0;  // 2^27
+  const double u = (double)(int)(BIG * u1) + u2;
+  return drj_qnorm(u / BIG);
+}
+__device__ __forceinline__ double drj_rnorm_from(double mu, double sigma, double z) {
+  if (isnan(mu) || !isfinite(sigma) || sigma < 0.0) return DRJ_NAN;
+  if (sigma == 0.0 || !isfinite(mu)) return mu;
+  return __dadd_rn(mu, __dmul_rn(sigma, z));  // mu + sigma * norm_rand(), product rounded as in R
+}
 __device__ __forceinline__ double drj_rnorm(double mu, double sigma, double u1, double u2) {
   if (isnan(mu) || !isfinite(sigma) || sigma < 0.0) return DRJ_NAN;
   if (sigma == 0.0 || !isfinite(mu)) return mu;
-  const double BIG = 134217728.0;  // 2^27
-  double u = (double)(int)(BIG * u1) + u2;
-  return __dadd_rn(mu, __dmul_rn(sigma, drj_qnorm(u / BIG)));  // mu + sigma * norm_rand(), product rounded as in R
+  return __dadd_rn(mu, __dmul_rn(sigma, drj_norm_rand(u1, u2)));
 }
 
 // ----------------------------------------------------------------------------- nmath
@@ -215,20 +225,23 @@ __device__ inline double dbinom_raw(double x, double n, double p, double q, int 
 
 namespace R {
 __device__ __forceinline__ double dnorm(double x, double mu, double sigma, int lg) {
+  // Regular arguments first, behind ONE fused test (a NaN anywhere fails a comparison); R's edge cases after it.  The
+  // regular path is the last line of R's dnorm4 with the same operations: the d = 50 multilevel model evaluates 55 of
+  // these per update, and the chain of seven separate tests and branches was 2/3 of each term's instructions (round-2 ncu).
+  const double z = (x - mu) / sigma;
+  if (sigma > 0.0 && sigma < DRJ_INF && fabs(z) < 2.6815615859885194e+154) {  // 2*sqrt(DBL_MAX)
+    // log(1) is exactly +0, so the select changes no bit; it lets the compiler drop the logarithm where sigma is the
+    // literal 1 (CUDA's log() is inline code, not a foldable builtin: the multilevel model spent half of ALL its
+    // instructions evaluating log(1.0), round 2 ncu)
+    if (lg) return -(DRJ_LN_SQRT_2PI + 0.5 * z * z + (sigma == 1.0 ? 0.0 : log(sigma)));
+    return 0.398942280401432677939946059934 * exp(-0.5 * z * z) / sigma;
+  }
   if (isnan(x) || isnan(mu) || isnan(sigma)) return x + mu + sigma;
   if (sigma < 0) return DRJ_NAN;
   if (!isfinite(sigma)) return drj_nmath::d0(lg);
   if (!isfinite(x) && mu == x) return DRJ_NAN;
   if (sigma == 0) return (x == mu) ? DRJ_INF : drj_nmath::d0(lg);
-  x = (x - mu) / sigma;
-  if (!isfinite(x)) return drj_nmath::d0(lg);
-  x = fabs(x);
-  if (x >= 2.6815615859885194e+154) return drj_nmath::d0(lg);  // 2*sqrt(DBL_MAX)
-  // log(1) is exactly +0, so the select changes no bit; it lets the compiler drop the logarithm where sigma is the
-  // literal 1 (CUDA's log() is inline code, not a foldable builtin: the d = 50 multilevel model spent half of ALL its
-  // instructions evaluating log(1.0) in its 55 unit-variance terms per update, round 2 ncu)
-  if (lg) return -(DRJ_LN_SQRT_2PI + 0.5 * x * x + (sigma == 1.0 ? 0.0 : log(sigma)));
-  return 0.398942280401432677939946059934 * exp(-0.5 * x * x) / sigma;
+  return drj_nmath::d0(lg);  // |z| infinite or beyond 2 sqrt(DBL_MAX)
 }
 
 __device__ __forceinline__ double dlnorm(double x, double meanlog, double sdlog, int lg) {

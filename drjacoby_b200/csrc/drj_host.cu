@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, do
 struct JitFuncs {
   CUmodule module = nullptr;
   CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr,
-             init_chain_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr;
+             init_chain_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr, lanes_sweep_cu = nullptr, spec_sweep_cu = nullptr;
 };
 
 struct drj_model {
@@ -339,6 +339,11 @@ struct drj_model {
   const void* team_sweep_fn = nullptr;
   const void* grid_init_fn = nullptr;   // grid-per-run variants (datum-form models)
   const void* grid_sweep_fn = nullptr;
+  const void* lanes_sweep_fn = nullptr; // a group of lanes per particle (drj_lanes.cuh): per-datum models and generic models with a lane form
+  int lanes = 0;                        // lanes per particle of that kernel (0 = the model has none)
+  int lanes_bpp = 0;                    // its shared-memory bytes per particle
+  const void* spec_sweep_fn = nullptr;  // one warp per chain, five updates in flight (drj_spec.cuh): one block, d <= 4
+  bool spec = false;                    // the model has that kernel
   // jit: the compiled cubin, loaded into a device's context on first use there (a model serves every device:
   // drj_run_mcmc_multi drives all GPUs from one model handle)
   std::vector<char> cubin;
@@ -360,6 +365,9 @@ struct BuiltinEntry {
   const void* init_chain_fn;
   const void* grid_init_fn;
   const void* grid_sweep_fn;
+  const void* lanes_sweep_fn;
+  int lanes, lanes_bpp;
+  const void* spec_sweep_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
@@ -368,7 +376,9 @@ struct BuiltinEntry {
         (const void*)drj_init_kernel<__VA_ARGS__>, (const void*)drj_sweep_kernel<__VA_ARGS__, false>, \
         DrjStreamKernel<__VA_ARGS__>::get(), DrjStreamKernel<__VA_ARGS__>::team_init(),                \
         DrjStreamKernel<__VA_ARGS__>::team_sweep(), (const void*)drj_init_chain_kernel<__VA_ARGS__>,   \
-        DrjStreamKernel<__VA_ARGS__>::grid_init(), DrjStreamKernel<__VA_ARGS__>::grid_sweep()          \
+        DrjStreamKernel<__VA_ARGS__>::grid_init(), DrjStreamKernel<__VA_ARGS__>::grid_sweep(),         \
+        DrjLanesKernel<__VA_ARGS__>::sweep(), DrjLanesKernel<__VA_ARGS__>::lanes,                      \
+        DrjLanesKernel<__VA_ARGS__>::bytes_per_particle, DrjSpecKernel<__VA_ARGS__>::sweep()           \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -482,6 +492,12 @@ static const char* const EMBED_SAMPLER =
 static const char* const EMBED_MODELS =
 #include "drj_embedded_models.inc"
     ;
+static const char* const EMBED_LANES =
+#include "drj_embedded_lanes.inc"
+    ;
+static const char* const EMBED_SPEC =
+#include "drj_embedded_spec.inc"
+    ;
 
 static uint64_t fnv1a(const std::string& s) {
   uint64_t h = 1469598103934665603ULL;
@@ -591,7 +607,18 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_sweep_grid(const __grid_constant__ DrjKernelArgs a) {\n"
        "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, false, DRJ_MODE_GRID>(a);\n"
        "}\n"
-       "extern \"C\" __global__ void drj_user_traits(int* out) { out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0; }\n";
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_lanes(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DrjLanesTraits<DRJ_USER_MODEL>::ok) drj_lanes_sweep_body<DRJ_USER_MODEL>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_SPEC_NT) drj_user_sweep_spec(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DrjSpecTraits<DRJ_USER_MODEL>::ok) drj_spec_sweep_body<DRJ_USER_MODEL>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void drj_user_traits(int* out) {\n"
+       "  out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0;\n"
+       "  out[1] = DrjLanesKernel<DRJ_USER_MODEL>::lanes;\n"
+       "  out[2] = DrjLanesKernel<DRJ_USER_MODEL>::bytes_per_particle;\n"
+       "  out[3] = DrjSpecTraits<DRJ_USER_MODEL>::ok ? 1 : 0;\n"
+       "}\n";
   return s;
 }
 
@@ -615,6 +642,8 @@ static int jit_functions(const drj_model* m, int device, const JitFuncs** out, d
       g_drv.ModuleGetFunction(&f.team_sweep_cu, f.module, "drj_user_sweep_team") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.grid_init_cu, f.module, "drj_user_init_grid") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.grid_sweep_cu, f.module, "drj_user_sweep_grid") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.lanes_sweep_cu, f.module, "drj_user_sweep_lanes") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.spec_sweep_cu, f.module, "drj_user_sweep_spec") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.init_chain_cu, f.module, "drj_user_init_chain") != CUDA_SUCCESS) {
     g_drv.ModuleUnload(f.module);
     return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
@@ -626,7 +655,7 @@ static int jit_functions(const drj_model* m, int device, const JitFuncs** out, d
 static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
   const double t0 = wall_now();
   const std::string src = make_jit_source(desc);
-  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|sm_100a|v6";
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|" + EMBED_LANES + "|" + EMBED_SPEC + "|sm_100a|v8";
   const uint64_t h1 = fnv1a(key_text), h2 = fnv1a_alt(key_text), klen = (uint64_t)key_text.size();
   char hex[40];
   snprintf(hex, sizeof(hex), "%016llx%08llx", (unsigned long long)h1, (unsigned long long)(h2 & 0xffffffffULL));
@@ -651,9 +680,9 @@ static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err)
     std::string why;
     if (!load_nvrtc(why)) return set_err(err, DRJ_ERR_COMPILE, "NVRTC unavailable: %s", why.c_str());
     nvrtcProgram prog;
-    const char* hdr_src[] = {EMBED_DEVICE, EMBED_SAMPLER, EMBED_MODELS};
-    const char* hdr_name[] = {"drj_device.cuh", "drj_sampler.cuh", "drj_models.cuh"};
-    nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "drj_jit_model.cu", 3, hdr_src, hdr_name);
+    const char* hdr_src[] = {EMBED_DEVICE, EMBED_SAMPLER, EMBED_MODELS, EMBED_LANES, EMBED_SPEC};
+    const char* hdr_name[] = {"drj_device.cuh", "drj_sampler.cuh", "drj_models.cuh", "drj_lanes.cuh", "drj_spec.cuh"};
+    nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "drj_jit_model.cu", 5, hdr_src, hdr_name);
     if (r != NVRTC_SUCCESS) return set_err(err, DRJ_ERR_COMPILE, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
     const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
     r = g_nvrtc.CompileProgram(prog, 4, opts);
@@ -685,16 +714,20 @@ static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err)
   const JitFuncs* jf = nullptr;
   int rc = jit_functions(m, m->device, &jf, err);
   if (rc) return rc;
-  {  // does the user's model use the per-datum form?
+  {  // does the user's model use the per-datum form?  does it have a lanes kernel?
     CUfunction traits = nullptr;
     int* d_flag = nullptr;
-    int h_flag = 0;
+    int h_flag[4] = {0, 0, 0, 0};
     if (g_drv.ModuleGetFunction(&traits, jf->module, "drj_user_traits") == CUDA_SUCCESS &&
-        cudaMalloc(&d_flag, sizeof(int)) == cudaSuccess) {
+        cudaMalloc(&d_flag, sizeof(h_flag)) == cudaSuccess) {
       void* params[] = {(void*)&d_flag};
       if (g_drv.LaunchKernel(traits, 1, 1, 1, 1, 1, 1, 0, nullptr, params, nullptr) == CUDA_SUCCESS &&
-          cudaMemcpy(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
-        m->datum_form = h_flag != 0;
+          cudaMemcpy(h_flag, d_flag, sizeof(h_flag), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        m->datum_form = h_flag[0] != 0;
+        m->lanes = h_flag[1];
+        m->lanes_bpp = h_flag[2];
+        m->spec = h_flag[3] != 0;
+      }
       cudaFree(d_flag);
     }
   }
@@ -725,6 +758,8 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       m->init_fn = b.init_fn; m->sweep_fn = b.sweep_fn; m->stream_fn = b.stream_fn; m->device = device;
       m->team_init_fn = b.team_init_fn; m->team_sweep_fn = b.team_sweep_fn; m->init_chain_fn = b.init_chain_fn;
       m->grid_init_fn = b.grid_init_fn; m->grid_sweep_fn = b.grid_sweep_fn;
+      m->lanes_sweep_fn = b.lanes_sweep_fn; m->lanes = b.lanes; m->lanes_bpp = b.lanes_bpp;
+      m->spec_sweep_fn = b.spec_sweep_fn; m->spec = b.spec_sweep_fn != nullptr;
       *out = m;
       return DRJ_OK;
     }
@@ -882,6 +917,11 @@ struct drj_session {
   bool team_ctas_forced = false;
   bool gridk = false;           // few particles x data >> L2: grid-per-run kernels (drj_sweep_item_grid), cooperative launch
   unsigned int* grid_bar = nullptr;
+  bool lanes = false;           // a group of lanes per particle (drj_lanes.cuh); the init kernels stay one thread per particle
+  int lanes_cpc = 0, lanes_grid = 0, lanes_threads = 0;
+  unsigned lanes_smem = 0;
+  bool spec = false;            // one warp per chain, five updates in flight (drj_spec.cuh); same init kernels, same data buffer
+  int spec_cpc = 0, spec_grid = 0;
   const JitFuncs* jf = nullptr; // source model: its kernels in this device's context
   unsigned dyn_smem = 0;        // dynamic shared memory of the model kernels: the data tile buffer
   double t_create = 0.0;
@@ -1020,6 +1060,32 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
     }
     return DRJ_OK;
   }
+  if (s->spec && sweep) {  // one warp per chain; the data tile buffer is the one-thread-per-particle kernels'
+    DrjKernelArgs a2 = s->a;
+    a2.chains_per_cta = s->spec_cpc;
+    void* p2[] = {(void*)&a2};
+    if (m->jit) {
+      CUresult cr = g_drv.LaunchKernel(s->jf->spec_sweep_cu, (unsigned)s->spec_grid, 1, 1, (unsigned)(32 * s->spec_cpc), 1, 1, s->dyn_smem,
+                                       (CUstream)s->stream, p2, nullptr);
+      if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
+    } else {
+      CUDA_TRY(cudaLaunchKernel(m->spec_sweep_fn, dim3(s->spec_grid), dim3(32 * s->spec_cpc), p2, s->dyn_smem, s->stream));
+    }
+    return DRJ_OK;
+  }
+  if (s->lanes && sweep) {  // its own geometry; the init kernels of the session use the one-thread-per-particle one
+    DrjKernelArgs a2 = s->a;
+    a2.chains_per_cta = s->lanes_cpc;
+    void* p2[] = {(void*)&a2};
+    if (m->jit) {
+      CUresult cr = g_drv.LaunchKernel(s->jf->lanes_sweep_cu, (unsigned)s->lanes_grid, 1, 1, (unsigned)s->lanes_threads, 1, 1, s->lanes_smem,
+                                       (CUstream)s->stream, p2, nullptr);
+      if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
+    } else {
+      CUDA_TRY(cudaLaunchKernel(m->lanes_sweep_fn, dim3(s->lanes_grid), dim3(s->lanes_threads), p2, s->lanes_smem, s->stream));
+    }
+    return DRJ_OK;
+  }
   if (m->jit) {
     CUresult cr = g_drv.LaunchKernel(!sweep ? s->jf->init_cu : (stream ? s->jf->stream_cu : s->jf->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1,
                                      s->dyn_smem, (CUstream)s->stream, params, nullptr);
@@ -1043,11 +1109,11 @@ static int solo_configure(drj_session* s, drj_error* err) {
   if ((size_t)s->dyn_smem + 24u * (size_t)s->D + 16384u <= 48u * 1024u) return DRJ_OK;  // static + dynamic within the default limit
   const drj_model* m = s->model;
   if (m->jit) {
-    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->stream_cu})
+    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->stream_cu, s->jf->spec_sweep_cu})
       if (f && g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
         return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed (dynamic shared memory %u bytes)", s->dyn_smem);
   } else {
-    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->stream_fn})
+    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->stream_fn, m->spec_sweep_fn})
       if (f) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
   }
   return DRJ_OK;
@@ -1402,6 +1468,93 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
       s->team_ctas = K;
       s->cpc = DRJ_TEAM_NT / R;  // slots per rung in a CTA
       s->nthreads = DRJ_TEAM_NT;
+    }
+  }
+
+  // one warp per chain, five updates in flight (drj_spec.cuh): a run of few single-rung chains of a small model -- the
+  // reference's everyday shape -- is a serial recurrence that one thread per chain runs at ~3 us per update.  The
+  // results are bitwise those of the one-thread-per-particle kernels, so the choice may depend on this shard's size.
+  {
+    long long longest = 0;
+    if (data) for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
+    bool can = model->spec && !s->team && !s->gridk && R == 1 && B == 1 && D <= 4 &&
+               (model->jit ? s->jf->spec_sweep_cu != nullptr : model->spec_sweep_fn != nullptr) &&
+               (!model->datum_form || longest <= 2LL * DRJ_TILE);
+    int n_free = 0;
+    for (int i = 0; i < D; ++i) {
+      if (cfg->skip_param[i]) continue;
+      ++n_free;
+      can = can && (cfg->block_ptr[i + 1] - cfg->block_ptr[i] == 1);  // every free parameter lists the one block
+    }
+    can = can && n_free >= 1;
+    bool want = C <= 1024;
+    if (cfg->flags & DRJ_FLAG_SPEC_KERNEL) want = true;
+    if (cfg->flags & (DRJ_FLAG_NO_SPEC_KERNEL | DRJ_FLAG_LANES_KERNEL)) want = false;
+    if (const char* e = getenv("DRJ_SPEC")) want = (e[0] == '1') ? true : (e[0] == '0' ? false : want);
+    if (can && want) {
+      s->spec = true;
+      s->stream_variant = false;
+      int w = (int)std::max<long long>(1, std::min<long long>(8, (C + 2LL * prop.multiProcessorCount - 1) / (2LL * prop.multiProcessorCount)));
+      if (cfg->chains_per_cta > 0) w = std::min(8, cfg->chains_per_cta);
+      s->spec_cpc = w;
+      s->spec_grid = (C + w - 1) / w;
+    }
+  }
+
+  // a group of lanes per particle (drj_lanes.cuh): generic models that declare a lane form (many parameters: the state moves
+  // from local to shared memory and the blocks are summed lane-parallel), and per-datum models when the run has too few
+  // particles to fill the machine with one thread each and the data is short (longer data: the cluster kernels above).
+  // Chosen from the WHOLE run's particle count, like the other families (the likelihood sums associate differently).
+  {
+    long long longest = 0;
+    if (data) for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
+    const int Lm = model->lanes;
+    const bool can = Lm > 0 && !s->team && !s->gridk && !s->spec && R <= std::min(32, DRJ_NT / std::max(1, Lm)) &&
+                     (model->jit ? s->jf->lanes_sweep_cu != nullptr : model->lanes_sweep_fn != nullptr);
+    bool want = model->datum_form ? (layout_P <= 2048 && longest <= 2LL * DRJ_TILE) : true;
+    if (cfg->flags & DRJ_FLAG_LANES_KERNEL) want = true;
+    if (cfg->flags & DRJ_FLAG_NO_LANES_KERNEL) want = false;
+    if (const char* e = getenv("DRJ_LANES")) want = (e[0] == '1') ? true : (e[0] == '0' ? false : want);
+    if (can && want) {
+      int stat = 0, optin = 0, per_sm = 0;
+      if (model->jit) {
+        CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuFuncGetAttribute", (void**)&FuncGetAttribute, cudaEnableDefault, &qr) == cudaSuccess && FuncGetAttribute)
+          FuncGetAttribute(&stat, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, s->jf->lanes_sweep_cu);
+        else stat = 16384;
+      } else {
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, model->lanes_sweep_fn));
+        stat = (int)fa.sharedSizeBytes;
+      }
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+      cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device);
+      const long long idx_bytes = 4LL * cfg->block_ptr[D] + 16;
+      const int np_max = DRJ_NT / Lm;
+      // two CTAs per SM when a whole chain fits in half of an SM's shared memory, else one
+      int cpc_l = 0;
+      for (long long budget : {(long long)per_sm / 2 - stat - 1024 - idx_bytes, (long long)optin - stat - 1024 - idx_bytes}) {
+        const int np_fit = (int)std::min<long long>(np_max, budget / model->lanes_bpp);
+        cpc_l = np_fit / R;
+        if (cpc_l >= 1) break;
+      }
+      if (cpc_l >= 1) {
+        if (cfg->chains_per_cta > 0) cpc_l = std::min(cpc_l, cfg->chains_per_cta);
+        else cpc_l = std::min(cpc_l, std::max(1, (int)((C + 2LL * prop.multiProcessorCount - 1) / (2LL * prop.multiProcessorCount))));  // few chains: spread them over the SMs
+        s->lanes = true;
+        s->stream_variant = false;
+        s->lanes_cpc = cpc_l;
+        s->lanes_threads = ((cpc_l * R * Lm + 31) / 32) * 32;
+        s->lanes_grid = (C + cpc_l - 1) / cpc_l;
+        s->lanes_smem = (unsigned)((long long)(s->lanes_threads / Lm) * model->lanes_bpp + idx_bytes);
+        if (model->jit) {
+          if (g_drv.FuncSetAttribute(s->jf->lanes_sweep_cu, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->lanes_smem) != CUDA_SUCCESS)
+            return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed for the lanes kernel (%u bytes of shared memory)", s->lanes_smem);
+        } else {
+          CUDA_TRY(cudaFuncSetAttribute(model->lanes_sweep_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->lanes_smem));
+        }
+      }
     }
   }
 

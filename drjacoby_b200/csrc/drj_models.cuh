@@ -6,6 +6,8 @@
 // (misc["block"], src/Particle.h:110) is the `block` argument.
 #pragma once
 #include "drj_sampler.cuh"
+#include "drj_lanes.cuh"
+#include "drj_spec.cuh"
 
 // per-datum form of  sum_i R::dnorm(x_i, mean, sd, log=TRUE) = -(n (log sqrt(2 pi) + log sd) + sum_i (x_i - mean)^2 / (2 sd^2)):
 // per datum  d = x - mean (1 DADD), acc = d*d + acc (1 DFMA); the scale 1/(2 sd^2) and the constants are
@@ -126,6 +128,36 @@ struct DrjModelMultilevel {
     return ret;
   }
   __device__ static __forceinline__ double logprior(const double*, const DrjList&) { return 0.0; }
+  // lane-split form (drj_lanes.cuh): lane l of 8 adds the terms l, l + 8, ... of the block, in order
+  static constexpr int LANES = 8;
+  __device__ static double loglike_lanes(const double* th, const DrjList& data, const DrjList&, int block, int lane) {
+    double ret = 0.0;
+    if (block == G + 1) {
+      // regular arguments: dnorm(z, 0, 1, log) = -(log sqrt(2 pi) + z^2 / 2), the same operations as R::dnorm's regular
+      // path, with ONE test for the whole lane instead of one per term; anything else takes R::dnorm term by term
+      constexpr int NT = (G + LANES - 1) / LANES;
+      bool regular = true;
+#pragma unroll
+      for (int k = 0; k < NT; ++k) {
+        const int i = lane + k * LANES;
+        if (i < G) {
+          const double z = th[i];
+          regular = regular && (fabs(z) < 2.6815615859885194e+154);
+          ret += -(DRJ_LN_SQRT_2PI + 0.5 * z * z);
+        }
+      }
+      if (!regular) {
+        ret = 0.0;
+        for (int i = lane; i < G; i += LANES) ret += R::dnorm(th[i], 0.0, 1.0, 1);
+      }
+    } else {
+      const double* x = data.item(block - 1);
+      const long long n = data.len(block - 1);
+      const double mu = th[block - 1];
+      for (long long i = lane; i < n; i += LANES) ret += R::dnorm(x[i], mu, 1.0, 1);
+    }
+    return ret;
+  }
 };
 
 // inst/extdata/blocks_loglike_logprior.cpp:5-58 with G groups (shipped: G = 6):

@@ -102,6 +102,12 @@ typedef struct drj_config {
 #define DRJ_FLAG_GRID_KERNEL 32     /* force the grid-per-run kernels (chains x rungs <= 256 over data far larger than L2: every SM
                                        streams 1/n_SM of the item once per sweep for all particles; datum-form models) */
 #define DRJ_FLAG_NO_GRID_KERNEL 64  /* never use the grid-per-run kernels */
+#define DRJ_FLAG_LANES_KERNEL 128   /* force the lanes kernel (a group of 8 or 32 lanes per particle; per-datum models and generic models with a
+                                       lane form, rungs <= 32): many parameters, or few particles over short data */
+#define DRJ_FLAG_NO_LANES_KERNEL 256 /* never use the lanes kernel */
+#define DRJ_FLAG_SPEC_KERNEL 512    /* force the speculative kernel (one warp per chain, five updates in flight: one rung, one block,
+                                       d <= 4, data <= 4096 points); results are bitwise those of one thread per particle */
+#define DRJ_FLAG_NO_SPEC_KERNEL 1024 /* never use the speculative kernel */
 
 /* A model = the user's loglike + logprior (inst/templates/cpp_template.cpp:4-18).  Either a
  * built-in model (builtin != NULL) or CUDA source compiled at run time with NVRTC for sm_100a:

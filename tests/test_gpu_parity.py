@@ -98,13 +98,18 @@ def blocks_case():
 CASES["blocks_chickwts"] = blocks_case()
 
 
+@pytest.mark.parametrize("family", ["auto", "thread"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_replay_matches_oracle(name, oracle):
+def test_replay_matches_oracle(name, family, oracle):
+    """`auto` = the kernel family the library picks for the shape (one warp per chain with five updates in flight for few
+    single-rung chains, drj_spec.cuh; a group of lanes per particle for the other few-particle per-datum cases and the
+    multilevel model, drj_lanes.cuh); `thread` = one thread per particle for every case."""
+    from drjacoby_b200 import _lib
     case = CASES[name]
     u = case.replay()
     ora = run_oracle(oracle, case, "replay", u)
-    gpu = run_gpu(case, "replay", u)
-    assert_parity(gpu, ora, RTOL, what=f"[{name}] ")
+    gpu = run_gpu(case, "replay", u, flags=(_lib.FLAG_NO_LANES_KERNEL | _lib.FLAG_NO_SPEC_KERNEL) if family == "thread" else 0)
+    assert_parity(gpu, ora, RTOL, what=f"[{name}/{family}] ")
 
 
 @pytest.mark.parametrize("name", ["example_n100", "example_rungs4", "doublewell_k2", "logistic_k3", "multilevel_g5",
@@ -220,6 +225,7 @@ def test_halfdomain_semantics():
 def test_random_configurations_match_oracle(oracle):
     """Differential fuzz: 40 random launch shapes / options (rungs 1..40, chains 1..37, data sizes around the
     accumulator-group, tile and residency boundaries, bounds, coupling on/off, hot draws, targets, seeds)."""
+    from drjacoby_b200 import _lib
     rng = np.random.Generator(np.random.Philox(2024))
     sizes = [1, 2, 7, 8, 9, 15, 16, 17, 63, 100, 255, 2047, 2048, 2049, 4095, 4096, 4097, 6151]
     for trial in range(40):
@@ -238,6 +244,8 @@ def test_random_configurations_match_oracle(oracle):
         kw = {}
         if rng.integers(0, 2):
             kw["iters_per_launch"] = int(rng.integers(1, 9))
+        # kernel family: the library's choice, one thread per particle, or a group of lanes per particle where it applies
+        kw["flags"] = int(rng.choice([0, _lib.FLAG_NO_LANES_KERNEL | _lib.FLAG_NO_SPEC_KERNEL, _lib.FLAG_LANES_KERNEL, _lib.FLAG_SPEC_KERNEL]))
         ora = run_oracle(oracle, case, "philox", seed=seed, chain_offset=off)
         gpu = run_gpu(case, "philox", seed=seed, chain_offset=off, **kw)
         assert_parity(gpu, ora, RTOL, what=f"[fuzz {trial}: {model} n={n} R={R} C={chains} {kw}] ")
