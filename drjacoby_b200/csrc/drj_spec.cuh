@@ -101,15 +101,43 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
   // this lane's node: n = lane (lane 0 doubles node 1), depth k, outcome of the ancestor at depth j = bit (k-1-j) of n
   const int n = lane ? lane : 1;
   const int k = 31 - __clz(n);
-  const int parent = n >> 1;
+  // What the node needs to know about its path never changes (the tree has the same shape in every pass):
+  //   rm_mask    bit j set = the ancestor at depth j proposed the node's own parameter (F free parameters in turn:
+  //              (k - j) % F == 0): a Robbins-Monro step of that parameter's bandwidth lies on the path;
+  //   anc[dl]    lane of the nearest ACCEPTED ancestor that proposed the parameter `dl` update slots before the node's
+  //              ((k - j) % F == dl), -1 = none: that parameter still has the value of the chain's state.
+  unsigned rm_mask = 0u;
+  int anc[D];
+#pragma unroll
+  for (int dl = 0; dl < D; ++dl) anc[dl] = -1;
+  if (F > 0) {
+    for (int j = 0; j < k; ++j) {  // ascending: the nearest ancestor overwrites
+      const int dl = (k - j) % F;
+      if (dl == 0) rm_mask |= 1u << j;
+      if ((n >> (k - 1 - j)) & 1) {
+#pragma unroll
+        for (int q = 0; q < D; ++q) if (q == dl) anc[q] = n >> (k - j);
+      }
+    }
+  }
+  // free slot and iteration offset of update (f0 + k) for every possible first slot f0 < F <= 4, one byte each
+  unsigned fk_tab = 0u, it_tab = 0u;
+  for (int f = 0; f < F; ++f) {
+    fk_tab |= (unsigned)((f + k) % F) << (8 * f);
+    it_tab |= (unsigned)((f + k) / F) << (8 * f);
+  }
 
   const long long V_total = F > 0 ? (long long)a.n_iter * F : 0;  // updates in this launch; update v = iteration * F + free slot
   int it = 0, f0 = 0;  // iteration-in-launch and free slot of the next update
   bool stopped = false;
   for (long long v0 = 0; v0 < V_total && !stopped; v0 += H) {
+    // an error reported by another chain stops this one at its next iteration boundary; the flag is read here, a pass
+    // early, so that the load's latency is not on the chain's critical path
+    unsigned long long seen_key = ~0ULL;
+    if (lane == 0) seen_key = *((volatile unsigned long long*)a.err_key);
     // ================= node (lane): the proposal of update v0 + k on the assumed path =================
     const long long vk = v0 + k;
-    const int itk = it + (f0 + k) / F, fk = (f0 + k) % F;
+    const int fk = (int)((fk_tab >> (8 * f0)) & 0xffu), itk = it + (int)((it_tab >> (8 * f0)) & 0xffu);
     const int ik = s_fl[fk];
     const bool live = vk < V_total;
     const int tk = a.iter0 + (live ? itk : it);
@@ -128,31 +156,22 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
     int bi = drj_picki<D>(bwi, ik);
 #pragma unroll
     for (int j = 0; j < H - 1; ++j) {
-      if (j < k && ((k - j) % F) == 0) {
+      if ((rm_mask >> j) & 1u) {
         const bool aj = (n >> (k - 1 - j)) & 1;
         lb = fma(aj ? (1.0 - target) : -target, rsqrt((double)bi), lb);
         ++bi;
       }
     }
     const double bw = exp(lb);
-    // phi of this parameter on the path: down the levels of the tree (a child takes its parent's, with the parent's
-    // proposal in place if the path says the parent was accepted)
-    double phiC[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) phiC[i] = phi[i];
-    double phi_p = drj_rnorm_from(drj_pick<D>(phiC, ik), bw, zq);  // (final for the root; deeper levels redo it below)
-    const int ipar = s_fl[(fk + F - 1) % F];  // the parameter the parent node proposed
+    const double gain = rsqrt((double)bi);  // of this node's own update
+    // phi' = phi + bandwidth * z, phi = the proposal of the nearest accepted ancestor on this parameter (down the levels
+    // of the tree: that ancestor's own phi' is final one level earlier) or the chain's
+    const int a0 = anc[0];
+    double phi_p = drj_rnorm_from(drj_pick<D>(phi, ik), bw, zq);  // (final when there is no such ancestor)
 #pragma unroll
     for (int lev = 1; lev < H; ++lev) {
-      const double pp = drj_shfl(phi_p, parent);
-      double pc[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) pc[i] = drj_shfl(phiC[i], parent);
-      if (k == lev) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) phiC[i] = ((n & 1) && i == ipar) ? pp : pc[i];
-        phi_p = drj_rnorm_from(drj_pick<D>(phiC, ik), bw, zq);
-      }
+      const double pp = drj_shfl(phi_p, a0 < 0 ? 0 : a0);
+      if (k == lev && a0 >= 0) phi_p = drj_rnorm_from(pp, bw, zq);
     }
     // phi_prop_to_theta_prop (Particle.cpp:55-74) and the logs of get_adjustment (Particle.cpp:103-124), all four
     // transform types in one instruction stream (the lanes of a warp propose different parameters)
@@ -168,42 +187,37 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
       hi_p = log(hi_arg);
       lo_p = log(lo_arg);
     }
-    // theta and the Jacobian logs of the current state on the path: the same pass down the levels
-    double thC[D], loC[D], hiC[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) { thC[i] = theta[i]; loC[i] = alo[i]; hiC[i] = ahi[i]; }
-#pragma unroll
-    for (int lev = 1; lev < H; ++lev) {
-      const double pt = drj_shfl(th_p, parent), pl = drj_shfl(lo_p, parent), ph = drj_shfl(hi_p, parent);
-      double ct[D], cl[D], ch[D];
-#pragma unroll
-      for (int i = 0; i < D; ++i) { ct[i] = drj_shfl(thC[i], parent); cl[i] = drj_shfl(loC[i], parent); ch[i] = drj_shfl(hiC[i], parent); }
-      if (k == lev) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) {
-          const bool take = (n & 1) && i == ipar;
-          thC[i] = take ? pt : ct[i]; loC[i] = take ? pl : cl[i]; hiC[i] = take ? ph : ch[i];
-        }
-      }
-    }
+    // the Jacobian logs of the current state of this parameter on the path, and the other parameters' values there
     double adj;
     {
-      const double alo_cur = drj_pick<D>(loC, ik), ahi_cur = drj_pick<D>(hiC, ik);
+      const double pl = drj_shfl(lo_p, a0 < 0 ? 0 : a0), ph = drj_shfl(hi_p, a0 < 0 ? 0 : a0);
+      const double alo_cur = a0 < 0 ? drj_pick<D>(alo, ik) : pl, ahi_cur = a0 < 0 ? drj_pick<D>(ahi, ik) : ph;
       adj = (tt == 0) ? 0.0 : (tt == 1) ? (hi_p - ahi_cur) : (tt == 2) ? (lo_p - alo_cur) : (hi_p + lo_p - ahi_cur - alo_cur);
     }
-    // likelihood and prior at theta' (Particle.h:107-118), the one-thread-per-particle evaluation
     double thn[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) thn[i] = (i == ik) ? th_p : thC[i];
+    for (int i = 0; i < D; ++i) thn[i] = (i == ik) ? th_p : theta[i];
+#pragma unroll
+    for (int dl = 1; dl < D; ++dl) {
+      const int src = anc[dl];
+      const double pt = drj_shfl(th_p, src < 0 ? 0 : src);
+      if (dl < F && src >= 0) {
+        const int fo = fk - dl + (fk < dl ? F : 0);  // the free slot `dl` updates before this node's
+        const int io = s_fl[fo];
+#pragma unroll
+        for (int i = 0; i < D; ++i) thn[i] = (i == io) ? pt : thn[i];
+      }
+    }
+    // likelihood and prior at theta' (Particle.h:107-118), the one-thread-per-particle evaluation
     const double ll_p = drj_eval_loglike<M, DRJ_MODE_SOLO>(T, a, thn, 1, 0);
     const double lp_p = M::logprior(thn, a.misc);
 
     // ================= the decisions, in order, along the path the chain takes =================
     int c = 1;  // node of the next update
     int err = 0;
+    const int nlev = (V_total - v0 < H) ? (int)(V_total - v0) : H;
 #pragma unroll 1
-    for (int lev = 0; lev < H; ++lev) {
-      if (v0 + lev >= V_total) break;
+    for (int lev = 0; lev < nlev; ++lev) {
       const int iu = s_fl[f0];  // (uniform) parameter of this update
       const double n_ll = drj_shfl(ll_p, c), n_lp = drj_shfl(lp_p, c), n_adj = drj_shfl(adj, c), n_lu = drj_shfl(lu, c);
       // NaN / +Inf guard (Particle.h:121-128)
@@ -219,11 +233,11 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
       const bool accept = (n_lu < MH) && (err == 0);
       // the node's proposal becomes the state; Robbins-Monro on the log scale (Particle.h:153-154,165-166)
       const double n_phi = drj_shfl(phi_p, c), n_th = drj_shfl(th_p, c), n_lo = drj_shfl(lo_p, c), n_hi = drj_shfl(hi_p, c);
+      const double n_gain = drj_shfl(gain, c);  // rsqrt(bandwidth index) as the node computed it on this very path
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         if (i == iu) {
-          const double gain = rsqrt((double)bwi[i]);
-          logbw[i] = fma(accept ? (1.0 - target) : -target, gain, logbw[i]);
+          logbw[i] = fma(accept ? (1.0 - target) : -target, n_gain, logbw[i]);
           bwi[i]++;
           if (accept) { phi[i] = n_phi; theta[i] = n_th; alo[i] = n_lo; ahi[i] = n_hi; }
         }
@@ -242,7 +256,7 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
           for (int i = 0; i < D; ++i) a.ring_theta[((long long)it * D + i) * a.chains + chain] = theta[i];
         }
         int stop = err;
-        if (lane == 0 && *((volatile unsigned long long*)a.err_key) != ~0ULL) stop = 1;
+        if (seen_key != ~0ULL) stop = 1;
         ++it;
         if (__any_sync(0xffffffffu, stop)) { stopped = true; break; }
       }

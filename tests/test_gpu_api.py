@@ -161,9 +161,12 @@ def test_nvrtc_errors_are_reported():
     assert e.value.code == 12 and "undefined_symbol" in str(e.value)
 
 
-def test_nvrtc_block_model_and_misc():
+def test_nvrtc_block_model_and_misc(monkeypatch):
     """Blocks + misc + several data items through the JIT path: the multilevel model written by hand
-    (inst/extdata/checks/multilevel_loglike_logprior.cpp) against the built-in."""
+    (inst/extdata/checks/multilevel_loglike_logprior.cpp) against the built-in, both on the one-thread-per-particle
+    kernels (the built-in declares a lane form and would otherwise run on the lanes kernel: equal within 1e-10, not
+    bitwise -- tests/test_gpu_lanes.py)."""
+    monkeypatch.setenv("DRJ_LANES", "0")
     G = 5
     rng = np.random.default_rng(5)
     data = {f"g{g + 1}": rng.normal(rng.normal(), 1.0, 5) for g in range(G)}

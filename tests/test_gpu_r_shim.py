@@ -79,7 +79,10 @@ def test_shim_replay_blocks_and_user_source(R):
     dnames = [f"g{g + 1}" for g in range(G)]
     out = R.dot_call("drjgpu_main", args_for(R, case, names, {"source": MULTILEVEL_SRC, "loglike": "loglike", "logprior": "logprior"}, dnames,
                                               replay=u, devices=[0]))
-    want = drj.run_raw(drj.Model(builtin="multilevel"), gpu_spec(case, "replay", u))
+    from drjacoby_b200 import _lib
+    # (the built-in declares a lane form and would run on the lanes kernel, equal within 1e-10 only: pin it to the
+    # one-thread-per-particle kernels the user's source runs on)
+    want = drj.run_raw(drj.Model(builtin="multilevel"), gpu_spec(case, "replay", u, flags=_lib.FLAG_NO_LANES_KERNEL))
     got = rd.chains_to_raw(R.to_py(out), G)
     for k, v in got.items():
         if k != "t_diff":
