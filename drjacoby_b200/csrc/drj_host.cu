@@ -1065,11 +1065,11 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
     a2.chains_per_cta = s->spec_cpc;
     void* p2[] = {(void*)&a2};
     if (m->jit) {
-      CUresult cr = g_drv.LaunchKernel(s->jf->spec_sweep_cu, (unsigned)s->spec_grid, 1, 1, (unsigned)(32 * s->spec_cpc), 1, 1, s->dyn_smem,
+      CUresult cr = g_drv.LaunchKernel(s->jf->spec_sweep_cu, (unsigned)s->spec_grid, 1, 1, (unsigned)(64 * s->spec_cpc), 1, 1, s->dyn_smem,
                                        (CUstream)s->stream, p2, nullptr);
       if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
     } else {
-      CUDA_TRY(cudaLaunchKernel(m->spec_sweep_fn, dim3(s->spec_grid), dim3(32 * s->spec_cpc), p2, s->dyn_smem, s->stream));
+      CUDA_TRY(cudaLaunchKernel(m->spec_sweep_fn, dim3(s->spec_grid), dim3(64 * s->spec_cpc), p2, s->dyn_smem, s->stream));
     }
     return DRJ_OK;
   }
@@ -1494,8 +1494,8 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     if (can && want) {
       s->spec = true;
       s->stream_variant = false;
-      int w = (int)std::max<long long>(1, std::min<long long>(8, (C + 2LL * prop.multiProcessorCount - 1) / (2LL * prop.multiProcessorCount)));
-      if (cfg->chains_per_cta > 0) w = std::min(8, cfg->chains_per_cta);
+      int w = (int)std::max<long long>(1, std::min<long long>(4, (C + 2LL * prop.multiProcessorCount - 1) / (2LL * prop.multiProcessorCount)));  // two warps per chain
+      if (cfg->chains_per_cta > 0) w = std::min(4, cfg->chains_per_cta);
       s->spec_cpc = w;
       s->spec_grid = (C + w - 1) / w;
     }

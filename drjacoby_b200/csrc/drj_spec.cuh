@@ -19,8 +19,9 @@
 //   * theta', the Jacobian logs, the log-likelihood and the log-prior of ALL 31 proposals are then evaluated at the
 //     same time, one proposal per lane, each with the code the one-thread-per-particle kernel uses
 //     (drj_eval_loglike / M::logprior);
-//   * the five decisions are then taken in order (four shuffles and the Metropolis-Hastings test per level), following
-//     the path the chain really takes; the other 26 evaluations are discarded.
+//   * every node then takes its own accept / reject decision, assuming its path (the current log-likelihood on the path is
+//     that of its nearest accepted ancestor), one ballot collects the 31 outcomes, and the path the chain really takes is
+//     five steps of integer arithmetic on that mask; its five proposals are committed, the other 26 discarded.
 // The warp advances exactly five updates per pass at the latency of ~one; the arithmetic of every update on the true
 // path is the arithmetic drj_sweep_body does, in the same order, so the results are BITWISE those of the
 // one-thread-per-particle kernels (tests/test_gpu_spec.py) -- the kernel family is a scheduling choice, not a numerical
@@ -30,7 +31,7 @@
 
 #define DRJ_SPEC_H 5     // updates in flight per pass (depth of the tree): 2^5 - 1 = 31 nodes, one per lane
 #define DRJ_SPEC_MAXD 4  // parameters (the per-lane path state lives in registers)
-#define DRJ_SPEC_NT 256  // threads per CTA = 8 chains
+#define DRJ_SPEC_NT 256  // threads per CTA = 4 chains x (the warp that runs the tree + the warp that draws ahead)
 
 template <class M>
 struct DrjSpecTraits {
@@ -58,7 +59,8 @@ template <class M>
 __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
   constexpr int D = M::D, H = DRJ_SPEC_H;
   static_assert(M::NBLOCK == 1 && D <= DRJ_SPEC_MAXD, "SPEC kernel: one block, d <= 4");
-  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 6;
+  const bool drawer = (tid >> 5) & 1;  // the chain's second warp: the random numbers of the NEXT pass (see below)
   const long long chain = (long long)blockIdx.x * a.chains_per_cta + wq;
   const bool valid = (wq < a.chains_per_cta) && (chain < a.chains);
   const long long cc = valid ? chain : 0;  // warps without a chain shadow chain 0 (they take part in the data staging)
@@ -68,6 +70,7 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
   __shared__ double s_tmin[D], s_tmax[D];
   __shared__ int s_trans[D], s_fl[D];
   __shared__ int s_nfree;
+  __shared__ double s_draw[DRJ_SPEC_NT / 64][2][2][32];  // [chain][pass parity][z, log u][node]
   if (tid == 0) {
     int f = 0;
     for (int i = 0; i < D; ++i) {
@@ -106,7 +109,10 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
   //              (k - j) % F == 0): a Robbins-Monro step of that parameter's bandwidth lies on the path;
   //   anc[dl]    lane of the nearest ACCEPTED ancestor that proposed the parameter `dl` update slots before the node's
   //              ((k - j) % F == dl), -1 = none: that parameter still has the value of the chain's state.
+  //   anc_any    lane of the nearest accepted ancestor of any parameter (-1 = none): whose log-likelihood and
+  //              log-prior are the current ones on the path.
   unsigned rm_mask = 0u;
+  int anc_any = -1;
   int anc[D];
 #pragma unroll
   for (int dl = 0; dl < D; ++dl) anc[dl] = -1;
@@ -115,6 +121,7 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
       const int dl = (k - j) % F;
       if (dl == 0) rm_mask |= 1u << j;
       if ((n >> (k - 1 - j)) & 1) {
+        anc_any = n >> (k - j);
 #pragma unroll
         for (int q = 0; q < D; ++q) if (q == dl) anc[q] = n >> (k - j);
       }
@@ -128,19 +135,14 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
   }
 
   const long long V_total = F > 0 ? (long long)a.n_iter * F : 0;  // updates in this launch; update v = iteration * F + free slot
-  int it = 0, f0 = 0;  // iteration-in-launch and free slot of the next update
-  bool stopped = false;
-  for (long long v0 = 0; v0 < V_total && !stopped; v0 += H) {
-    // an error reported by another chain stops this one at its next iteration boundary; the flag is read here, a pass
-    // early, so that the load's latency is not on the chain's critical path
-    unsigned long long seen_key = ~0ULL;
-    if (lane == 0) seen_key = *((volatile unsigned long long*)a.err_key);
-    // ================= node (lane): the proposal of update v0 + k on the assumed path =================
-    const long long vk = v0 + k;
-    const int fk = (int)((fk_tab >> (8 * f0)) & 0xffu), itk = it + (int)((it_tab >> (8 * f0)) & 0xffu);
+  // The standard normal draw of a proposal and log u of its acceptance test depend on nothing but the update's counter
+  // (Philox, qnorm, a logarithm: a quarter of a pass's instructions, all at the head of its dependent chain).  The
+  // chain's second warp forms them one pass AHEAD, node by node, into a double-buffered shared-memory table; the
+  // two warps meet at one CTA barrier per pass.
+  auto draw = [&](long long v0_, int it_, int f0_, int parity) {
+    const int fk = (int)((fk_tab >> (8 * f0_)) & 0xffu), itk = it_ + (int)((it_tab >> (8 * f0_)) & 0xffu);
     const int ik = s_fl[fk];
-    const bool live = vk < V_total;
-    const int tk = a.iter0 + (live ? itk : it);
+    const int tk = a.iter0 + ((v0_ + k < V_total) ? itk : it_);  // (nodes past the end of the launch: any valid row)
     double u1, u2, u3;
     if (a.rng_mode) {
       const double* qq = a.replay + (cc * a.replay_T + (tk - 1)) * a.replay_U + 3 * (long long)fk;
@@ -149,8 +151,30 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
       DrjU4 x4 = drj_philox4x32_10(gchain_lo, (unsigned)tk, (unsigned)ik, gchain_hi << 8, k0, k1);
       u1 = drj_u32_to_unif(x4.x); u2 = drj_u32_to_unif(x4.y); u3 = drj_u32_to_unif(x4.z);
     }
-    const double zq = drj_norm_rand(u1, u2);
-    const double lu = log(u3);
+    s_draw[wq][parity][0][lane] = drj_norm_rand(u1, u2);
+    s_draw[wq][parity][1][lane] = log(u3);
+  };
+  int it = 0, f0 = 0;  // iteration-in-launch and free slot of the next update (the drawer: of the pass it draws for)
+  int err = 0;         // first error of the current iteration (the run stops at the iteration's end)
+  if (drawer && V_total > 0) draw(0, 0, 0, 0);
+  __syncthreads();
+  int parity = 0;
+  for (long long v0 = 0; v0 < V_total; v0 += H, parity ^= 1) {
+    int stop = 0;
+    if (drawer) {
+      it += (f0 + H) / F;
+      f0 = (f0 + H) % F;
+      if (v0 + H < V_total) draw(v0 + H, it, f0, parity ^ 1);
+    } else {
+    // an error reported by another chain stops this one at its next iteration boundary; the flag is read here, a pass
+    // early, so that the load's latency is not on the chain's critical path
+    unsigned long long seen_key = ~0ULL;
+    if (lane == 0) seen_key = *((volatile unsigned long long*)a.err_key);
+    // ================= node (lane): the proposal of update v0 + k on the assumed path =================
+    const int fk = (int)((fk_tab >> (8 * f0)) & 0xffu);
+    const int ik = s_fl[fk];
+    const double zq = s_draw[wq][parity][0][lane];
+    const double lu = s_draw[wq][parity][1][lane];
     // Robbins-Monro along the path: one step per ancestor that updated this parameter (Particle.h:153-154,165-166)
     double lb = drj_pick<D>(logbw, ik);
     int bi = drj_picki<D>(bwi, ik);
@@ -212,59 +236,92 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
     const double ll_p = drj_eval_loglike<M, DRJ_MODE_SOLO>(T, a, thn, 1, 0);
     const double lp_p = M::logprior(thn, a.misc);
 
-    // ================= the decisions, in order, along the path the chain takes =================
-    int c = 1;  // node of the next update
-    int err = 0;
-    const int nlev = (V_total - v0 < H) ? (int)(V_total - v0) : H;
-#pragma unroll 1
-    for (int lev = 0; lev < nlev; ++lev) {
-      const int iu = s_fl[f0];  // (uniform) parameter of this update
-      const double n_ll = drj_shfl(ll_p, c), n_lp = drj_shfl(lp_p, c), n_adj = drj_shfl(adj, c), n_lu = drj_shfl(lu, c);
-      // NaN / +Inf guard (Particle.h:121-128)
-      if (err == 0 && valid) {
-        if (isnan(n_ll) || n_ll == DRJ_INF) err = DRJ_ERR_LOGLIKE_BAD;
-        else if (isnan(n_lp) || n_lp == DRJ_INF) err = DRJ_ERR_LOGPRIOR_BAD;
-        if (err && lane == c) drj_report(a, err, it, chain, 0, iu, p, thn, D);
-      }
+    // ================= the decisions =================
+    // Every node takes ITS OWN decision at once, assuming its path: the current log-likelihood / log-prior on the path
+    // are those of its nearest accepted ancestor (a fixed lane) or the chain's.  One ballot collects the 31 outcomes; the
+    // path the chain really takes is then five steps of integer arithmetic on that mask (no shuffle, no floating point
+    // in the serial part), and on the true path every assumption held, so the decisions are the serial ones.
+    int n_err = 0;  // NaN / +Inf guard (Particle.h:121-128)
+    if (isnan(ll_p) || ll_p == DRJ_INF) n_err = DRJ_ERR_LOGLIKE_BAD;
+    else if (isnan(lp_p) || lp_p == DRJ_INF) n_err = DRJ_ERR_LOGPRIOR_BAD;
+    bool n_acc;
+    {
+      const double pl = drj_shfl(ll_p, anc_any < 0 ? 0 : anc_any), pp = drj_shfl(lp_p, anc_any < 0 ? 0 : anc_any);
+      const double ll_cur = anc_any < 0 ? ll : pl, lp_cur = anc_any < 0 ? lp : pp;
       // Metropolis-Hastings (Particle.h:131-139): explicitly rounded product and sums, left to right
       double MH;
-      if (beta == 0.0) MH = __dadd_rn(n_lp - lp, n_adj);
-      else MH = __dadd_rn(__dadd_rn(__dmul_rn(beta, n_ll - ll), n_lp - lp), n_adj);
-      const bool accept = (n_lu < MH) && (err == 0);
-      // the node's proposal becomes the state; Robbins-Monro on the log scale (Particle.h:153-154,165-166)
-      const double n_phi = drj_shfl(phi_p, c), n_th = drj_shfl(th_p, c), n_lo = drj_shfl(lo_p, c), n_hi = drj_shfl(hi_p, c);
-      const double n_gain = drj_shfl(gain, c);  // rsqrt(bandwidth index) as the node computed it on this very path
+      if (beta == 0.0) MH = __dadd_rn(lp_p - lp_cur, adj);
+      else MH = __dadd_rn(__dadd_rn(__dmul_rn(beta, ll_p - ll_cur), lp_p - lp_cur), adj);
+      n_acc = (lu < MH) && (n_err == 0);
+    }
+    const unsigned acc_mask = __ballot_sync(0xffffffffu, n_acc);
+    const unsigned err_mask = __ballot_sync(0xffffffffu, n_err != 0 && valid);
+    const int nlev = (V_total - v0 < H) ? (int)(V_total - v0) : H;
+    int path[H];
+    unsigned bits = 0u;
+    int err_lev = -1;
+    {
+      int c = 1;
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        if (i == iu) {
-          logbw[i] = fma(accept ? (1.0 - target) : -target, n_gain, logbw[i]);
-          bwi[i]++;
-          if (accept) { phi[i] = n_phi; theta[i] = n_th; alo[i] = n_lo; ahi[i] = n_hi; }
-        }
-      }
-      ll = accept ? n_ll : ll;
-      lp = accept ? n_lp : lp;
-      acc += accept ? 1 : 0;
-      c = 2 * c + (accept ? 1 : 0);
-      if (++f0 == F) {
-        f0 = 0;
-        // ---- end of an iteration: store (main.cpp:165-173), abort on error (Rcpp::stop in the reference)
-        if (valid && lane == 0) {
-          a.ring_ll[(long long)it * a.chains + chain] = ll;  // (one rung: store_pt and save_hot_draws address the same slots)
-          a.ring_lp[(long long)it * a.chains + chain] = lp;
-#pragma unroll
-          for (int i = 0; i < D; ++i) a.ring_theta[((long long)it * D + i) * a.chains + chain] = theta[i];
-        }
-        int stop = err;
-        if (seen_key != ~0ULL) stop = 1;
-        ++it;
-        if (__any_sync(0xffffffffu, stop)) { stopped = true; break; }
+      for (int lev = 0; lev < H; ++lev) {
+        path[lev] = c;
+        if (err == 0 && err_lev < 0 && ((err_mask >> c) & 1u)) err_lev = lev;  // the first bad proposal on the true path
+        // (after an error every update of the iteration is rejected, and the run stops at the iteration's end)
+        const unsigned ok = ((acc_mask >> c) & 1u) & ((err == 0 && err_lev < 0) ? 1u : 0u);
+        bits |= ok << lev;
+        c = 2 * c + (int)ok;
       }
     }
+    // ================= commit, level by level (all sources are known: the shuffles below are independent) =================
+    bool stopped = false;
+#pragma unroll
+    for (int lev = 0; lev < H; ++lev) {
+      if (lev < nlev && !stopped) {
+        const int c = path[lev];
+        const bool accept = (bits >> lev) & 1u;
+        const int iu = s_fl[f0];  // (uniform) parameter of this update
+        if (lev == err_lev) {
+          err = __shfl_sync(0xffffffffu, n_err, c);
+          if (lane == c) drj_report(a, n_err, it, chain, 0, iu, p, thn, D);
+        }
+        // the node's proposal becomes the state; Robbins-Monro on the log scale (Particle.h:153-154,165-166)
+        const double n_phi = drj_shfl(phi_p, c), n_th = drj_shfl(th_p, c), n_lo = drj_shfl(lo_p, c), n_hi = drj_shfl(hi_p, c);
+        const double n_ll = drj_shfl(ll_p, c), n_lp = drj_shfl(lp_p, c);
+        const double n_gain = drj_shfl(gain, c);  // rsqrt(bandwidth index) as the node computed it on this very path
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          if (i == iu) {
+            logbw[i] = fma(accept ? (1.0 - target) : -target, n_gain, logbw[i]);
+            bwi[i]++;
+            if (accept) { phi[i] = n_phi; theta[i] = n_th; alo[i] = n_lo; ahi[i] = n_hi; }
+          }
+        }
+        ll = accept ? n_ll : ll;
+        lp = accept ? n_lp : lp;
+        acc += accept ? 1 : 0;
+        if (++f0 == F) {
+          f0 = 0;
+          // ---- end of an iteration: store (main.cpp:165-173), abort on error (Rcpp::stop in the reference)
+          if (valid && lane == 0) {
+            a.ring_ll[(long long)it * a.chains + chain] = ll;  // (one rung: store_pt and save_hot_draws address the same slots)
+            a.ring_lp[(long long)it * a.chains + chain] = lp;
+#pragma unroll
+            for (int i = 0; i < D; ++i) a.ring_theta[((long long)it * D + i) * a.chains + chain] = theta[i];
+          }
+          int halt = err;
+          if (seen_key != ~0ULL) halt = 1;
+          ++it;
+          if (__any_sync(0xffffffffu, halt)) stopped = true;
+        }
+      }
+    }
+    stop = stopped ? 1 : 0;
+    }  // (the warp that runs the tree)
+    if (__syncthreads_or(stop)) break;  // the next pass's draws are in place; an aborted chain takes its CTA with it
   }
 
   // ---- write state back
-  if (valid && lane == 0) {
+  if (valid && lane == 0 && !drawer) {
 #pragma unroll
     for (int i = 0; i < D; ++i) {
       const long long o = (long long)i * P + p;
