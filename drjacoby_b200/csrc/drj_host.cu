@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, do
 struct JitFuncs {
   CUmodule module = nullptr;
   CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr,
-             init_chain_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr, lanes_sweep_cu = nullptr, spec_sweep_cu = nullptr;
+             init_chain_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr, lanes_sweep_cu = nullptr, spec5_cu = nullptr, spec7_cu = nullptr;
 };
 
 struct drj_model {
@@ -342,7 +342,8 @@ struct drj_model {
   const void* lanes_sweep_fn = nullptr; // a group of lanes per particle (drj_lanes.cuh): per-datum models and generic models with a lane form
   int lanes = 0;                        // lanes per particle of that kernel (0 = the model has none)
   int lanes_bpp = 0;                    // its shared-memory bytes per particle
-  const void* spec_sweep_fn = nullptr;  // one warp per chain, five updates in flight (drj_spec.cuh): one block, d <= 4
+  const void* spec5_fn = nullptr;       // one CTA per chain, five / seven updates in flight (drj_spec.cuh): one block, d <= 4
+  const void* spec7_fn = nullptr;
   bool spec = false;                    // the model has that kernel
   // jit: the compiled cubin, loaded into a device's context on first use there (a model serves every device:
   // drj_run_mcmc_multi drives all GPUs from one model handle)
@@ -367,7 +368,8 @@ struct BuiltinEntry {
   const void* grid_sweep_fn;
   const void* lanes_sweep_fn;
   int lanes, lanes_bpp;
-  const void* spec_sweep_fn;
+  const void* spec5_fn;
+  const void* spec7_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
@@ -378,7 +380,8 @@ struct BuiltinEntry {
         DrjStreamKernel<__VA_ARGS__>::team_sweep(), (const void*)drj_init_chain_kernel<__VA_ARGS__>,   \
         DrjStreamKernel<__VA_ARGS__>::grid_init(), DrjStreamKernel<__VA_ARGS__>::grid_sweep(),         \
         DrjLanesKernel<__VA_ARGS__>::sweep(), DrjLanesKernel<__VA_ARGS__>::lanes,                      \
-        DrjLanesKernel<__VA_ARGS__>::bytes_per_particle, DrjSpecKernel<__VA_ARGS__>::sweep()           \
+        DrjLanesKernel<__VA_ARGS__>::bytes_per_particle, DrjSpecKernel<__VA_ARGS__>::sweep5(),         \
+        DrjSpecKernel<__VA_ARGS__>::sweep7()                                                           \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -610,8 +613,11 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_lanes(const __grid_constant__ DrjKernelArgs a) {\n"
        "  if constexpr (DrjLanesTraits<DRJ_USER_MODEL>::ok) drj_lanes_sweep_body<DRJ_USER_MODEL>(a);\n"
        "}\n"
-       "extern \"C\" __global__ void __launch_bounds__(DRJ_SPEC_NT) drj_user_sweep_spec(const __grid_constant__ DrjKernelArgs a) {\n"
-       "  if constexpr (DrjSpecTraits<DRJ_USER_MODEL>::ok) drj_spec_sweep_body<DRJ_USER_MODEL>(a);\n"
+       "extern \"C\" __global__ void __launch_bounds__(32) drj_user_sweep_spec5(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DrjSpecTraits<DRJ_USER_MODEL>::ok) drj_spec_sweep_body<DRJ_USER_MODEL, 5>(a);\n"
+       "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(1 << DRJ_SPEC_DEEP) drj_user_sweep_spec7(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  if constexpr (DrjSpecTraits<DRJ_USER_MODEL>::ok) drj_spec_sweep_body<DRJ_USER_MODEL, DRJ_SPEC_DEEP>(a);\n"
        "}\n"
        "extern \"C\" __global__ void drj_user_traits(int* out) {\n"
        "  out[0] = DRJ_USER_MODEL::DATUM_FORM ? 1 : 0;\n"
@@ -643,7 +649,8 @@ static int jit_functions(const drj_model* m, int device, const JitFuncs** out, d
       g_drv.ModuleGetFunction(&f.grid_init_cu, f.module, "drj_user_init_grid") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.grid_sweep_cu, f.module, "drj_user_sweep_grid") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.lanes_sweep_cu, f.module, "drj_user_sweep_lanes") != CUDA_SUCCESS ||
-      g_drv.ModuleGetFunction(&f.spec_sweep_cu, f.module, "drj_user_sweep_spec") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.spec5_cu, f.module, "drj_user_sweep_spec5") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.spec7_cu, f.module, "drj_user_sweep_spec7") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.init_chain_cu, f.module, "drj_user_init_chain") != CUDA_SUCCESS) {
     g_drv.ModuleUnload(f.module);
     return set_err(err, DRJ_ERR_COMPILE, "kernels not found in the compiled module");
@@ -655,7 +662,7 @@ static int jit_functions(const drj_model* m, int device, const JitFuncs** out, d
 static int jit_compile(const drj_model_desc* desc, drj_model* m, drj_error* err) {
   const double t0 = wall_now();
   const std::string src = make_jit_source(desc);
-  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|" + EMBED_LANES + "|" + EMBED_SPEC + "|sm_100a|v8";
+  const std::string key_text = src + "|" + EMBED_DEVICE + "|" + EMBED_SAMPLER + "|" + EMBED_MODELS + "|" + EMBED_LANES + "|" + EMBED_SPEC + "|sm_100a|v9";
   const uint64_t h1 = fnv1a(key_text), h2 = fnv1a_alt(key_text), klen = (uint64_t)key_text.size();
   char hex[40];
   snprintf(hex, sizeof(hex), "%016llx%08llx", (unsigned long long)h1, (unsigned long long)(h2 & 0xffffffffULL));
@@ -759,7 +766,7 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       m->team_init_fn = b.team_init_fn; m->team_sweep_fn = b.team_sweep_fn; m->init_chain_fn = b.init_chain_fn;
       m->grid_init_fn = b.grid_init_fn; m->grid_sweep_fn = b.grid_sweep_fn;
       m->lanes_sweep_fn = b.lanes_sweep_fn; m->lanes = b.lanes; m->lanes_bpp = b.lanes_bpp;
-      m->spec_sweep_fn = b.spec_sweep_fn; m->spec = b.spec_sweep_fn != nullptr;
+      m->spec5_fn = b.spec5_fn; m->spec7_fn = b.spec7_fn; m->spec = b.spec5_fn != nullptr;
       *out = m;
       return DRJ_OK;
     }
@@ -920,8 +927,8 @@ struct drj_session {
   bool lanes = false;           // a group of lanes per particle (drj_lanes.cuh); the init kernels stay one thread per particle
   int lanes_cpc = 0, lanes_grid = 0, lanes_threads = 0;
   unsigned lanes_smem = 0;
-  bool spec = false;            // one warp per chain, five updates in flight (drj_spec.cuh); same init kernels, same data buffer
-  int spec_cpc = 0, spec_grid = 0;
+  bool spec = false;            // one CTA per chain, 5 or 7 updates in flight (drj_spec.cuh); same init kernels, same data buffer
+  int spec_depth = 0;
   const JitFuncs* jf = nullptr; // source model: its kernels in this device's context
   unsigned dyn_smem = 0;        // dynamic shared memory of the model kernels: the data tile buffer
   double t_create = 0.0;
@@ -1060,16 +1067,14 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
     }
     return DRJ_OK;
   }
-  if (s->spec && sweep) {  // one warp per chain; the data tile buffer is the one-thread-per-particle kernels'
-    DrjKernelArgs a2 = s->a;
-    a2.chains_per_cta = s->spec_cpc;
-    void* p2[] = {(void*)&a2};
+  if (s->spec && sweep) {  // one CTA of 2^depth threads per chain; the data tile buffer is the one-thread-per-particle kernels'
+    const unsigned nt = 1u << (s->spec_depth == 7 ? DRJ_SPEC_DEEP : 5);
     if (m->jit) {
-      CUresult cr = g_drv.LaunchKernel(s->jf->spec_sweep_cu, (unsigned)s->spec_grid, 1, 1, (unsigned)(64 * s->spec_cpc), 1, 1, s->dyn_smem,
-                                       (CUstream)s->stream, p2, nullptr);
+      CUresult cr = g_drv.LaunchKernel(s->spec_depth == 7 ? s->jf->spec7_cu : s->jf->spec5_cu, (unsigned)s->C, 1, 1, nt, 1, 1, s->dyn_smem,
+                                       (CUstream)s->stream, params, nullptr);
       if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
     } else {
-      CUDA_TRY(cudaLaunchKernel(m->spec_sweep_fn, dim3(s->spec_grid), dim3(64 * s->spec_cpc), p2, s->dyn_smem, s->stream));
+      CUDA_TRY(cudaLaunchKernel(s->spec_depth == 7 ? m->spec7_fn : m->spec5_fn, dim3(s->C), dim3(nt), params, s->dyn_smem, s->stream));
     }
     return DRJ_OK;
   }
@@ -1109,11 +1114,11 @@ static int solo_configure(drj_session* s, drj_error* err) {
   if ((size_t)s->dyn_smem + 24u * (size_t)s->D + 16384u <= 48u * 1024u) return DRJ_OK;  // static + dynamic within the default limit
   const drj_model* m = s->model;
   if (m->jit) {
-    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->stream_cu, s->jf->spec_sweep_cu})
+    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->stream_cu, s->jf->spec5_cu, s->jf->spec7_cu})
       if (f && g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
         return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed (dynamic shared memory %u bytes)", s->dyn_smem);
   } else {
-    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->stream_fn, m->spec_sweep_fn})
+    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->stream_fn, m->spec5_fn, m->spec7_fn})
       if (f) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
   }
   return DRJ_OK;
@@ -1471,14 +1476,14 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     }
   }
 
-  // one warp per chain, five updates in flight (drj_spec.cuh): a run of few single-rung chains of a small model -- the
+  // one CTA per chain, five or seven updates in flight (drj_spec.cuh): a run of few single-rung chains of a small model -- the
   // reference's everyday shape -- is a serial recurrence that one thread per chain runs at ~3 us per update.  The
   // results are bitwise those of the one-thread-per-particle kernels, so the choice may depend on this shard's size.
   {
     long long longest = 0;
     if (data) for (int k = 0; k < data->n_items; ++k) longest = std::max<long long>(longest, data->lengths[k]);
     bool can = model->spec && !s->team && !s->gridk && R == 1 && B == 1 && D <= 4 &&
-               (model->jit ? s->jf->spec_sweep_cu != nullptr : model->spec_sweep_fn != nullptr) &&
+               (model->jit ? s->jf->spec5_cu != nullptr : model->spec5_fn != nullptr) &&
                (!model->datum_form || longest <= 2LL * DRJ_TILE);
     int n_free = 0;
     for (int i = 0; i < D; ++i) {
@@ -1494,10 +1499,10 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     if (can && want) {
       s->spec = true;
       s->stream_variant = false;
-      int w = (int)std::max<long long>(1, std::min<long long>(4, (C + 2LL * prop.multiProcessorCount - 1) / (2LL * prop.multiProcessorCount)));  // two warps per chain
-      if (cfg->chains_per_cta > 0) w = std::min(4, cfg->chains_per_cta);
-      s->spec_cpc = w;
-      s->spec_grid = (C + w - 1) / w;
+      // seven updates in flight (four warps per chain, one per scheduler) while the chains leave the SMs room for it,
+      // five (one warp per chain) for more chains
+      s->spec_depth = (C <= 2LL * prop.multiProcessorCount) ? 7 : 5;
+      if (const char* e = getenv("DRJ_SPEC_DEPTH")) { const int v = atoi(e); if (v == 5 || v == 7) s->spec_depth = v; }
     }
   }
 

@@ -1,5 +1,5 @@
-"""The SPEC kernel (drjacoby_b200/csrc/drj_spec.cuh): one warp per chain, the next five updates evaluated speculatively
-(a binary tree of 31 proposals, one per lane), for the reference's everyday shape -- few single-rung chains of a small
+"""The SPEC kernels (drjacoby_b200/csrc/drj_spec.cuh): one CTA per chain, the next five or seven updates evaluated
+speculatively (a binary tree of 31 / 127 proposals, one per thread), for the reference's everyday shape -- few single-rung chains of a small
 model (run_mcmc defaults, R/main.R:213-216; BASELINE configs[0] is ONE chain over n = 100).
 
 Every update on the path the chain really takes is the arithmetic of the one-thread-per-particle kernel in the same
@@ -60,8 +60,11 @@ def assert_same_bits(a, b, what):
             assert np.array_equal(a[k], b[k]), f"{what}: {k} differs"
 
 
+@pytest.mark.parametrize("depth", ["5", "7"])
 @pytest.mark.parametrize("name", sorted(SPEC_CASES))
-def test_spec_is_bitwise_one_thread_per_particle(name):
+def test_spec_is_bitwise_one_thread_per_particle(name, depth, monkeypatch):
+    """Both tree depths: five updates in flight (one warp per chain) and seven (four warps per chain)."""
+    monkeypatch.setenv("DRJ_SPEC_DEPTH", depth)
     case = SPEC_CASES[name]
     spec = run_gpu(case, "philox", seed=31, chain_offset=(1 << 32) + 7, flags=lib().FLAG_SPEC_KERNEL)
     solo = run_gpu(case, "philox", seed=31, chain_offset=(1 << 32) + 7, flags=thread_flags())
@@ -106,10 +109,15 @@ def test_spec_launch_split_and_geometry_are_bitwise_invariant():
     case = SPEC_CASES["forty_chains"]
     F = lib().FLAG_SPEC_KERNEL
     ref = run_gpu(case, "philox", seed=21, chain_offset=10, flags=F)
-    for kw in ({"iters_per_launch": 1}, {"iters_per_launch": 3}, {"iters_per_launch": 7}, {"chains_per_cta": 1},
-               {"chains_per_cta": 3}, {"chains_per_cta": 8}):
-        out = run_gpu(case, "philox", seed=21, chain_offset=10, flags=F, **kw)
-        assert_same_bits(ref, out, f"[spec {kw}]")
+    import os
+    for kw, depth in (({"iters_per_launch": 1}, "5"), ({"iters_per_launch": 3}, "7"), ({"iters_per_launch": 7}, "5"),
+                      ({"iters_per_launch": 2}, "7"), ({}, "5"), ({}, "7")):
+        os.environ["DRJ_SPEC_DEPTH"] = depth
+        try:
+            out = run_gpu(case, "philox", seed=21, chain_offset=10, flags=F, **kw)
+        finally:
+            os.environ.pop("DRJ_SPEC_DEPTH", None)
+        assert_same_bits(ref, out, f"[spec {kw} depth {depth}]")
     lo, hi = 11, 29
     shard = Case(case.model, case.tmin, case.tmax, data=case.data, chains=hi - lo, burnin=case.burnin, samples=case.samples,
                  init=case.init[lo:hi], target=case.target)
