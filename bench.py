@@ -156,25 +156,31 @@ def named_configs(world, x_long=None, only=None):
     cfgs = {
         "K1": dict(ex, what="BASELINE configs[0]: normal model (mu, sigma), n = 100, 1 chain x 1 rung, burnin 1e3 + samples 1e4", data=[x100],
                    beta=[1.0], chains=1, burnin=1000, samples=10000, full=True, scale="replicas", flop=FLOP_PER_DATUM * 100 + W_FIXED,
-                   bound="latency", cpu_chains=1),
+                   bound="latency", cpu_chains=1,
+                   kernel="drj_sweep_kernel_spec<example, 7>: one CTA per chain, seven updates in flight (127 speculative proposals per pass)"),
         "K2": dict(model="doublewell", tmin=[-2.0, 30.0], tmax=[2.0, 30.0], what="BASELINE configs[1]: double well, 64 chains x 20 rungs, alpha = 2, "
                    "Metropolis coupling, burnin 1e3 + samples 1e4", data=[], beta=(np.linspace(0, 1, 20) ** 2.0), chains=64, burnin=1000, samples=10000,
-                   full=True, scale="strong", flop=W_FIXED + 6, bound="fp64", cpu_chains=64),
+                   full=True, scale="strong", flop=W_FIXED + 6, bound="fp64", cpu_chains=64,
+                   kernel="drj_sweep_kernel<doublewell, STREAM=0>: one thread per particle"),
         "K3": dict(model="logistic", tmin=[1.0, 1.0, 50.0], tmax=[100.0, 2.0, 200.0], what="BASELINE configs[2]: logistic growth fit to population_data "
                    "(100-step map + 20 Poisson terms per evaluation), 1024 chains x 10 rungs, burnin 1e3 + samples 1e4",
                    data=[POPULATION["pop"], POPULATION["time"]], beta=np.linspace(0, 1, 10), chains=1024, burnin=1000, samples=10000, full=True,
-                   scale="strong", flop=100 * 4 + 20 * 40 + W_FIXED, bound="fp64", cpu_chains=1024),
+                   scale="strong", flop=100 * 4 + 20 * 40 + W_FIXED, bound="fp64", cpu_chains=1024,
+                   kernel="drj_sweep_kernel<logistic, STREAM=0>: one thread per particle"),
         "K4": dict(model="multilevel", tmin=[-5.0] * G, tmax=[5.0] * G, what="BASELINE configs[3]: multilevel block-update model, 50 parameters in 51 "
                    "overlapping blocks, 4096 chains x 16 rungs; timed window 200 iterations after 50 (a full 1e3 + 1e4 run is 3.6e10 updates)",
                    data=data50, blocks=[[g + 1, G + 1] for g in range(G)], beta=np.linspace(0, 1, 16), chains=4096, burnin=51, samples=200,
-                   warm=50, full=False, scale="strong", flop=(5 + 50) * 4 + 51 + W_FIXED, bound="fp64", cpu_chains=None),
+                   warm=50, full=False, scale="strong", flop=(5 + 50) * 4 + 51 + W_FIXED, bound="fp64", cpu_chains=None,
+                   kernel="drj_sweep_kernel_lanes<multilevel<50>>: 8 lanes per particle, state in shared memory"),
         "n100": dict(ex, what="normal model, n = 100 (the K1 data), 12,500 chains x 32 rungs per GPU: the regime the 1e10 updates/s/box target refers to "
                      "(SURVEY 8(d))", data=[x100], beta=np.linspace(0, 1, RUNGS), chains=CHAINS_PER_GPU * world, burnin=101, samples=500, warm=100,
-                     ipl=100, full=False, scale="weak", flop=FLOP_PER_DATUM * 100 + W_FIXED, bound="fp64", cpu_chains=None),
+                     ipl=100, full=False, scale="weak", flop=FLOP_PER_DATUM * 100 + W_FIXED, bound="fp64", cpu_chains=None,
+                     kernel="drj_sweep_kernel<example, STREAM=0>: one thread per particle, data resident in shared memory"),
         "n4096": dict(ex, what="normal model, n = 4096 (largest data set resident in shared memory), 12,500 chains x 32 rungs per GPU: "
                       ">= 1e10 updates/s/box AND >= 70 % of the FP64 roofline", data=[synth_data(4096)], beta=np.linspace(0, 1, RUNGS),
                       chains=CHAINS_PER_GPU * world, burnin=21, samples=40, warm=20, ipl=20, full=False, scale="weak",
-                      flop=FLOP_PER_DATUM * 4096, bound="fp64", cpu_chains=None),
+                      flop=FLOP_PER_DATUM * 4096, bound="fp64", cpu_chains=None,
+                      kernel="drj_sweep_kernel<example, STREAM=1>: one thread per particle, data resident in shared memory"),
     }
     if x_long is not None:
         n = x_long.size
@@ -182,7 +188,8 @@ def named_configs(world, x_long=None, only=None):
             cfgs[f"hbm_{c}x1"] = dict(ex, what=f"HBM-bound regime: normal model, n = {n} ({8 * n / 1e6:.0f} MB >> L2), {c} chain(s) x 1 rung per GPU on the "
                                       "grid-per-run kernels: every SM streams 1/148 of the data once per sweep for all chains", data=[x_long], beta=[1.0],
                                       chains=c * world, burnin=11, samples=20, warm=10, ipl=10, full=False, scale="weak", flop=FLOP_PER_DATUM * n,
-                                      bound="hbm", bytes_per_sweep=8.0 * n, cpu_chains=None)
+                                      bound="hbm", bytes_per_sweep=8.0 * n, cpu_chains=None,
+                                      kernel="drj_sweep_kernel_grid<example>: the whole grid per run, 64 KB TMA chunks, one grid barrier per sweep")
     if only:
         cfgs = {k: v for k, v in cfgs.items() if k in only}
     return cfgs
@@ -231,7 +238,7 @@ def run_named_config(drj, name, c, rank, world, device, fp64_peak, hbm_peak, red
     jobs = world if c["scale"] == "replicas" else 1
     updates = jobs * c["chains"] * R * d_free * (T - warm)
     value = updates / (dev_ms * 1e-3)
-    out = {"workload": c["what"], "chains_total": jobs * c["chains"], "rungs": R, "free_params": d_free, "iterations_timed": T - warm,
+    out = {"workload": c["what"], "kernel": c.get("kernel"), "chains_total": jobs * c["chains"], "rungs": R, "free_params": d_free, "iterations_timed": T - warm,
            "full_run": bool(c["full"]), "scaling": c["scale"], "value": value, "unit": UNIT, "chain_rung_updates_per_sec": value / d_free,
            "device_ms": dev_ms, "sweep_kernel_ms": sweep_ms, "wall_s": wall, "gpu_launches_this_rank": launches}
     if c["bound"] == "hbm":

@@ -175,7 +175,7 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
     // of the tree: that ancestor's own phi' is final, and published, one level earlier) or the chain's
     const int a0 = anc[0];
     double phi_p = drj_rnorm_from(drj_pick<D>(phi, ik), bw, zq);  // (final when there is no such ancestor)
-#pragma unroll
+#pragma unroll  // (rolled, this loop and the commit loop below make the kernel 17 % smaller and 3-8 % slower, same-box A/B)
     for (int lev = 1; lev < H; ++lev) {
       if (k == lev - 1) t_phi[n] = phi_p;
       __syncthreads();
