@@ -62,3 +62,21 @@ __device__ double logprior(const double* params, const DrjList& misc) {
 //   #define DRJ_USER_MODEL MyModel
 //
 // datum() must ADD its term to acc (the sampler keeps 8 partial sums and adds them at the end).
+//
+// ---------------------------------------------------------------------------------------------
+// OPTIONAL: the lane form, for models with many parameters (more than 8) whose blocks are sums of terms.
+// One GPU thread per chain x rung keeps theta and the block likelihoods of such a model in its own (slow) local
+// memory and adds every block up alone.  If the model struct also says how to split a block over LANES threads,
+// a particle is run by a group of LANES lanes of a warp, its state lives once in shared memory, and the lanes add
+// their shares of a block in parallel (their partial sums are combined in a fixed order).  Add to the struct
+// (DATUM_FORM = false; loglike() and logprior() as above):
+//
+//     static constexpr int LANES = 8;          // 4, 8, 16 or 32
+//     __device__ static double loglike_lanes(const double* params, const DrjList& data, const DrjList& misc,
+//                                            int block, int lane) {
+//       // the terms of loglike(params, data, misc, block) that lane `lane` adds up; over lane = 0 .. LANES-1 every
+//       // term exactly once, e.g. for a block that sums over a data vector:
+//       double r = 0;
+//       for (long long i = lane; i < data.len(block - 1); i += LANES) r += R::dnorm(data.item(block - 1)[i], params[block - 1], 1.0, true);
+//       return r;
+//     }

@@ -165,3 +165,47 @@ def test_lanes_k1_full_length(oracle):
     ora = run_oracle(oracle, case, "philox", seed=5)
     gpu = run_gpu(case, "philox", seed=5, flags=lib().FLAG_LANES_KERNEL)
     assert_parity(gpu, ora, RTOL, what="[lanes/k1 full length] ")
+
+
+def test_lanes_user_model_with_a_lane_form(oracle):
+    """A user's many-parameter model that declares the lane form (cuda_template.cu, last section), compiled with NVRTC:
+    the multilevel model with 12 groups written by hand.  Replay parity with the CPU oracle on the lanes kernel, and
+    the lanes kernel really runs (its sums associate differently from one thread per particle)."""
+    import drjacoby_b200 as drj
+    G = 12
+    src = r'''
+struct MyMultilevel {
+  static constexpr int D = DRJ_D, NBLOCK = DRJ_NBLOCK;
+  static constexpr bool DATUM_FORM = false;
+  static constexpr int LANES = 8;
+  __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int block) {
+    double ret = 0.0;
+    if (block == D + 1) { for (int i = 0; i < D; ++i) ret += R::dnorm(th[i], 0.0, 1.0, true); }
+    else { const double* x = data.item(block - 1); for (long long i = 0; i < data.len(block - 1); ++i) ret += R::dnorm(x[i], th[block - 1], 1.0, true); }
+    return ret;
+  }
+  __device__ static double loglike_lanes(const double* th, const DrjList& data, const DrjList&, int block, int lane) {
+    double ret = 0.0;
+    if (block == D + 1) { for (int i = lane; i < D; i += LANES) ret += R::dnorm(th[i], 0.0, 1.0, true); }
+    else { const double* x = data.item(block - 1); for (long long i = lane; i < data.len(block - 1); i += LANES) ret += R::dnorm(x[i], th[block - 1], 1.0, true); }
+    return ret;
+  }
+  __device__ static double logprior(const double*, const DrjList&) { return 0.0; }
+};
+#define DRJ_USER_MODEL MyMultilevel
+'''
+    case = multilevel_case(G, 3, 4, burnin=25, samples=25)
+    user = drj.Model(source=src)
+    u = case.replay()
+    ora = run_oracle(oracle, case, "replay", u)
+    lanes = run_gpu(case, "replay", u, model=user, flags=lib().FLAG_LANES_KERNEL)
+    auto = run_gpu(case, "replay", u, model=user)
+    solo = run_gpu(case, "replay", u, model=user, flags=lib().FLAG_NO_LANES_KERNEL)
+    assert_parity(lanes, ora, RTOL, what="[lanes/jit lane form] ")
+    assert_parity(solo, ora, RTOL, what="[thread/jit lane form] ")
+    differs = False
+    for k in lanes:
+        if k != "t_diff":
+            assert np.array_equal(lanes[k], auto[k]), k  # a model with a lane form runs on the lanes kernel by default
+            differs = differs or not np.array_equal(lanes[k], solo[k])
+    assert differs
