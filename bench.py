@@ -185,9 +185,10 @@ def named_configs(world, x_long=None, only=None):
     if x_long is not None:
         n = x_long.size
         for c in (1, 5):
-            cfgs[f"hbm_{c}x1"] = dict(ex, what=f"HBM-bound regime: normal model, n = {n} ({8 * n / 1e6:.0f} MB >> L2), {c} chain(s) x 1 rung per GPU on the "
-                                      "grid-per-run kernels: every SM streams 1/148 of the data once per sweep for all chains", data=[x_long], beta=[1.0],
-                                      chains=c * world, burnin=11, samples=20, warm=10, ipl=10, full=False, scale="weak", flop=FLOP_PER_DATUM * n,
+            cfgs[f"hbm_{c}x1"] = dict(ex, what=f"HBM-bound regime: normal model, n = {n} ({8 * n / 1e6:.0f} MB >> L2), {c} chain(s) x 1 rung on the "
+                                      "grid-per-run kernels: every SM streams 1/148 of the data once per sweep for all chains (at N > 1 every GPU "
+                                      "runs its own such job: a run of this kind is a handful of chains)", data=[x_long], beta=[1.0],
+                                      chains=c, burnin=11, samples=20, warm=10, ipl=10, full=False, scale="replicas", flop=FLOP_PER_DATUM * n,
                                       bound="hbm", bytes_per_sweep=8.0 * n, cpu_chains=None,
                                       kernel="drj_sweep_kernel_grid<example>: the whole grid per run, 64 KB TMA chunks, one grid barrier per sweep")
     if only:

@@ -824,11 +824,11 @@ extern "C" double drj_model_compile_seconds(const drj_model* m) { return m ? m->
 // size, instead of cudaFree / cudaMalloc: a series of runs of one shape (the usual way run_mcmc is used, and
 // what bench.py does) then costs no allocation time, and -- measured -- the memory-bound summary kernels of the
 // next run no longer slow down several-fold now and then right after tens of GB were freed and re-allocated.
-// Blocks >= 1 MB only, at most DRJ_POOL_GB (default 48) GB per process, everything is released when an
-// allocation fails or drj_release_cached_memory() is called.
+// At most DRJ_POOL_GB (default 48) GB per device, everything is released when an allocation fails or
+// drj_release_cached_memory() is called.
 struct PoolBlock { void* p; size_t bytes; int device; };
 static std::vector<PoolBlock> g_pool;
-static size_t g_pool_bytes = 0;
+static std::map<int, size_t> g_pool_bytes;  // cached bytes per device (the cap is per device: each GPU has its own 180 GB)
 static std::mutex g_pool_mutex;
 
 static size_t pool_cap() {
@@ -849,7 +849,7 @@ static size_t pool_release(int device) {  // device < 0: all devices
       cudaSetDevice(g_pool[i].device);
       cudaFree(g_pool[i].p);
       freed += g_pool[i].bytes;
-      g_pool_bytes -= g_pool[i].bytes;
+      g_pool_bytes[g_pool[i].device] -= g_pool[i].bytes;
       g_pool[i] = g_pool.back();
       g_pool.pop_back();
     } else ++i;
@@ -863,13 +863,25 @@ static size_t pool_cached(int device) {
   for (const PoolBlock& b : g_pool) if (b.device == device) n += b.bytes;
   return n;
 }
+// size of the block that serves a request: small requests are rounded up to a power of two (>= 256 bytes) so that the
+// few dozen small buffers of a session find a block of their class whatever the run's shape; large ones are kept exact
+// (a series of runs of one shape asks for the same sizes).  EVERY device allocation of a session goes through the pool:
+// cudaMalloc / cudaFree take a process-wide lock (and cudaFree synchronises the device), so with one host thread per GPU
+// the ~50 small allocations and frees of each session serialised across the devices (8 GPUs: +0.18 s on a 0.22 s run).
+static size_t pool_size(size_t bytes) {
+  if (bytes >= (1u << 20)) return bytes;
+  size_t c = 256;
+  while (c < bytes) c <<= 1;
+  return c;
+}
 static cudaError_t pool_alloc(int device, size_t bytes, void** out) {
-  if (bytes >= (1u << 20)) {
+  bytes = pool_size(bytes);
+  {
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     for (size_t i = 0; i < g_pool.size(); ++i)
       if (g_pool[i].device == device && g_pool[i].bytes == bytes) {
         *out = g_pool[i].p;
-        g_pool_bytes -= bytes;
+        g_pool_bytes[device] -= bytes;
         g_pool[i] = g_pool.back();
         g_pool.pop_back();
         return cudaSuccess;
@@ -884,11 +896,12 @@ static cudaError_t pool_alloc(int device, size_t bytes, void** out) {
 }
 static void pool_free(int device, void* p, size_t bytes) {
   if (!p) return;
-  if (bytes >= (1u << 20)) {
+  bytes = pool_size(bytes);
+  {
     std::lock_guard<std::mutex> lk(g_pool_mutex);
-    if (g_pool_bytes + bytes <= pool_cap()) {
+    if (g_pool_bytes[device] + bytes <= pool_cap()) {
       g_pool.push_back({p, bytes, device});
-      g_pool_bytes += bytes;
+      g_pool_bytes[device] += bytes;
       return;
     }
   }
@@ -942,10 +955,10 @@ struct drj_session {
 static cudaError_t scratch_get(drj_session* s, int slot, size_t bytes, double** out) {
   bytes = std::max<size_t>(bytes, 8);
   if (s->scratch_bytes[slot] < bytes) {
-    if (s->scratch[slot]) cudaFree(s->scratch[slot]);
+    if (s->scratch[slot]) pool_free(s->cfg.device, s->scratch[slot], s->scratch_bytes[slot]);
     s->scratch[slot] = nullptr;
     s->scratch_bytes[slot] = 0;
-    cudaError_t e = cudaMalloc(&s->scratch[slot], bytes);
+    cudaError_t e = pool_alloc(s->cfg.device, bytes, &s->scratch[slot]);
     if (e != cudaSuccess) return e;
     s->scratch_bytes[slot] = bytes;
   }
@@ -1100,6 +1113,22 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
                               params, s->dyn_smem, s->stream));
   }
   return DRJ_OK;
+}
+
+// cudaGetDeviceProperties is slow (it queries the driver for ~100 attributes under a process-wide lock): once per device
+static cudaError_t device_props(int device, cudaDeviceProp* out) {
+  static std::mutex mu;
+  static std::map<int, cudaDeviceProp> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(device);
+  if (it == cache.end()) {
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) return e;
+    it = cache.emplace(device, p).first;
+  }
+  *out = it->second;
+  return cudaSuccess;
 }
 
 static int prop_sms(const drj_session* s) {
@@ -1330,7 +1359,7 @@ extern "C" void drj_session_destroy(drj_session* s) {
   cudaSetDevice(s->cfg.device);
   cudaStreamSynchronize(s->stream);  // nothing of this session may still be running when its buffers are reused
   for (auto& pb : s->allocs) pool_free(s->cfg.device, pb.first, pb.second);
-  for (void* p : s->scratch) if (p) cudaFree(p);
+  for (int k = 0; k < 12; ++k) if (s->scratch[k]) pool_free(s->cfg.device, s->scratch[k], s->scratch_bytes[k]);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev2) cudaEventDestroy(s->ev2);
@@ -1362,7 +1391,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   // ---- launch geometry: all rungs of a chain in one CTA, as many chains per CTA as fit in DRJ_NT
   // threads, but no more than needed to give every SM a few CTAs
   cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+  CUDA_TRY(device_props(cfg->device, &prop));
   const int max_cpc = std::max(1, DRJ_NT / R);
   int cpc = cfg->chains_per_cta > 0 ? std::min(cfg->chains_per_cta, max_cpc) : max_cpc;
   if (cfg->chains_per_cta <= 0) {
@@ -1993,7 +2022,7 @@ static int copy_series(drj_session* s, double* dst, const double* src, long long
   const int n_keep = (n + thin - 1) / thin;
   const size_t bytes = sizeof(double) * (size_t)n_series * n_keep * w;
   double* tmp = nullptr;
-  CUDA_TRY(cudaMalloc(&tmp, std::max<size_t>(bytes, 8)));
+  CUDA_TRY(pool_alloc(s->cfg.device, std::max<size_t>(bytes, 8), (void**)&tmp));
   const long long total = n_series * n_keep * w;
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148 * 16));
   drj_thin_rows<<<grid, 256, 0, s->stream>>>(src, tmp, n_series, n, n_keep, w, thin);
@@ -2001,7 +2030,7 @@ static int copy_series(drj_session* s, double* dst, const double* src, long long
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, s->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-  cudaFree(tmp);
+  pool_free(s->cfg.device, tmp, std::max<size_t>(bytes, 8));
   CUDA_TRY(e);
   return DRJ_OK;
 }
@@ -2034,12 +2063,12 @@ extern "C" int drj_session_download_thinned(drj_session* s, int thin, drj_output
 #undef D2H
   if (out->bw_final) {
     double* tmp = nullptr;
-    CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * (size_t)s->P * s->D));
+    CUDA_TRY(pool_alloc(s->cfg.device, sizeof(double) * (size_t)s->P * s->D, (void**)&tmp));
     drj_export_bw<<<(unsigned)((s->P + 255) / 256), 256, 0, s->stream>>>(s->a.logbw, s->P, s->D, tmp);
     s->aux_launches++;
     cudaError_t e = cudaMemcpyAsync(out->bw_final, tmp, sizeof(double) * (size_t)s->P * s->D, cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(tmp);
+    pool_free(s->cfg.device, tmp, sizeof(double) * (size_t)s->P * s->D);
     CUDA_TRY(e);
   }
   if (out->t_diff) {
