@@ -166,7 +166,7 @@ def named_configs(world, x_long=None, only=None):
                    "(100-step map + 20 Poisson terms per evaluation), 1024 chains x 10 rungs, burnin 1e3 + samples 1e4",
                    data=[POPULATION["pop"], POPULATION["time"]], beta=np.linspace(0, 1, 10), chains=1024, burnin=1000, samples=10000, full=True,
                    scale="strong", flop=100 * 4 + 20 * 40 + W_FIXED, bound="fp64", cpu_chains=1024,
-                   kernel="drj_sweep_kernel<logistic, STREAM=0>: one thread per particle"),
+                   kernel="drj_sweep_kernel_lanes<logistic>: 4 lanes per particle (every lane walks the map, the Poisson terms 4 at a time)"),
         "K4": dict(model="multilevel", tmin=[-5.0] * G, tmax=[5.0] * G, what="BASELINE configs[3]: multilevel block-update model, 50 parameters in 51 "
                    "overlapping blocks, 4096 chains x 16 rungs; timed window 200 iterations after 50 (a full 1e3 + 1e4 run is 3.6e10 updates)",
                    data=data50, blocks=[[g + 1, G + 1] for g in range(G)], beta=np.linspace(0, 1, 16), chains=4096, burnin=51, samples=200,

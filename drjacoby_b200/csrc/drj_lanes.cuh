@@ -39,7 +39,7 @@
 #define DRJ_MODE_LANES 3
 
 // A generic model opts in to the lane-split form with
-//   static constexpr int LANES = 8;   // lanes per particle: 4, 8, 16 or 32
+//   static constexpr int LANES = 8;   // lanes per particle: 2, 4, 8, 16 or 32
 //   __device__ static double loglike_lanes(const double* theta, const DrjList& data, const DrjList& misc, int block, int lane);
 // = the terms of loglike(theta, data, misc, block) that lane `lane` of LANES adds up (their sum over the lanes is the
 // block's log-likelihood).  Per-datum models need nothing: their split is lane l -> data l, l + 32, ...
@@ -142,7 +142,7 @@ __device__ __forceinline__ void drj_lanes_sweep_body(const DrjKernelArgs& a) {
   typedef DrjLanesTraits<M> TR;
   constexpr int L = TR::L, D = TR::D, B = TR::B, RBS = TR::RBS, RGS = TR::RGS;
   constexpr bool BATCH = TR::BATCH;
-  static_assert(L == 4 || L == 8 || L == 16 || L == 32, "LANES must be 4, 8, 16 or 32");
+  static_assert(L == 2 || L == 4 || L == 8 || L == 16 || L == 32, "LANES must be 2, 4, 8, 16 or 32");
   const int R = a.rungs;
   const int tid = threadIdx.x, lane = tid & (L - 1), q = tid / L;
   const int NP = blockDim.x / L;

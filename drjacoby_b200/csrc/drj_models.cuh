@@ -215,6 +215,15 @@ struct DrjModelTestFile {
   }
 };
 
+// one step of the discrete logistic map x <- r x (1 - x / K) (vignettes/getting_model_fits.Rmd:80-83), the body of a
+// 100-step dependent chain: written as r x - (r / K) x^2 -- two independent products and one fma, a dependent depth of
+// two FP64 instructions instead of the three of the literal form (and no division on the chain: c = r / K once).  A few
+// ulp per step on a map that contracts onto its fixed point, far inside the 1e-10 parity gate (tests: logistic_k3, the
+// K3 full-size case, the getting_model_fits vignette's acceptance rates).
+__device__ __forceinline__ double drj_logistic_step(double x, double r, double c) {
+  return fma(-(c * x), x, r * x);
+}
+
 // vignettes/getting_model_fits.Rmd:72-104 -- params (N_0, r, N_max), data (pop, time)  (K3)
 struct DrjModelLogistic {
   static constexpr int D = 3, NBLOCK = 1;
@@ -222,7 +231,7 @@ struct DrjModelLogistic {
   __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
     const double N_0 = th[0], r = th[1], N_max = th[2];
     const double K = N_max * r / (r - 1.0);
-    const double inv_K = 1.0 / K;
+    const double c = r / K;
     const double* pop = data.item(0);
     const double* time = data.item(1);
     const int n = (int)data.len(0);
@@ -234,16 +243,62 @@ struct DrjModelLogistic {
     for (int j = 0; j < n; ++j) {
       const int tj = (int)time[j];
       if (tj < step) { x = N_0; step = 1; }
-      // x / K as x * (1 / K): the division sat on the 100-step dependent chain (~10x the latency of a multiply);
-      // <= 1 ulp per step on a contracting map, far inside the 1e-10 parity gate (tests: logistic_k3, K3 full size,
-      // the getting_model_fits vignette rates)
-      for (; step < tj; ++step) x = r * x * (1.0 - x * inv_K);
+      for (; step < tj; ++step) x = drj_logistic_step(x, r, c);
       ret += R::dpois(pop[j], x, 1);
     }
     return ret;
   }
   __device__ static double logprior(const double* th, const DrjList&) {
+    // R::dunif(x, a, b, log) with the three constant widths' logarithms written out (CUDA's log() is inline code the
+    // compiler does not fold: three logarithms of constants per update were 4 % of the K3 run, round-2 ncu)
+    const bool in = th[0] >= 1.0 && th[0] <= 100.0 && th[1] >= 1.0 && th[1] <= 2.0 && th[2] >= 50.0 && th[2] <= 200.0;
+    if (in) return -4.59511985013458992685 + -0.0 + -5.01063529409625575354;  // -(log 99 + log 1 + log 150)
     return R::dunif(th[0], 1.0, 100.0, 1) + R::dunif(th[1], 1.0, 2.0, 1) + R::dunif(th[2], 50.0, 200.0, 1);
+  }
+  // lane-split form (drj_lanes.cuh): the 100-step map is a serial recurrence every lane walks (same instructions),
+  // keeping the state at ITS observation times j = lane, lane + LANES, ...; the Poisson terms -- 20 x ~150
+  // instructions, 3/4 of the serial evaluation -- are then evaluated LANES at a time.
+#ifndef DRJ_LOGISTIC_LANES
+#define DRJ_LOGISTIC_LANES 4  // K3 (1024 x 10) measured: 2 lanes 2.8e8, 4 lanes 5.2e8, 8 lanes 3.8e8, 16 lanes 3.0e8 updates/s; one thread 2.4e8
+#endif
+  static constexpr int LANES = DRJ_LOGISTIC_LANES;
+  __device__ static double loglike_lanes(const double* th, const DrjList& data, const DrjList&, int, int lane) {
+    const double N_0 = th[0], r = th[1], N_max = th[2];
+    const double K = N_max * r / (r - 1.0);
+    const double c = r / K;
+    const double* pop = data.item(0);
+    const double* time = data.item(1);
+    const int n = (int)data.len(0);
+    constexpr int MAXQ = 32 / LANES;  // observations per lane kept in registers (n <= 32); more: the serial walk per term below
+    double xs[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) xs[q] = 0.0;
+    double x = N_0;
+    int step = 1;
+    bool monotone = n <= MAXQ * LANES;
+    for (int j = 0; j < n && monotone; ++j) {  // uniform over the lanes
+      const int tj = (int)time[j];
+      if (tj < step) { monotone = false; break; }
+      for (; step < tj; ++step) x = drj_logistic_step(x, r, c);
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q) xs[q] = (j == lane + q * LANES) ? x : xs[q];
+    }
+    double ret = 0.0;
+    if (monotone) {
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q) {
+        const int j = lane + q * LANES;
+        if (j < n) ret += R::dpois(pop[j], xs[q], 1);
+      }
+    } else {  // times that go backwards, or a long series: every lane walks to each of its own observations
+      for (int j = lane; j < n; j += LANES) {
+        const int tj = (int)time[j];
+        x = N_0;
+        for (step = 1; step < tj; ++step) x = drj_logistic_step(x, r, c);
+        ret += R::dpois(pop[j], x, 1);
+      }
+    }
+    return ret;
   }
 };
 

@@ -10,7 +10,7 @@ independent of the launch geometry, the launch split and the sharding of chains.
 import numpy as np
 import pytest
 
-from helpers import Case, assert_parity, beta_ladder, gpu_spec, rel_close, run_gpu, run_oracle
+from helpers import POPULATION, Case, assert_parity, beta_ladder, gpu_spec, rel_close, run_gpu, run_oracle
 from test_gpu_parity import CASES, multilevel_case, normal_data
 
 pytestmark = pytest.mark.gpu
@@ -48,7 +48,13 @@ LANES_CASES = {
     # a fixed parameter (skip_param: no random numbers consumed), more chains than fit one CTA
     "sigma_fixed": Case("example", [-10, 2.0], [10, 2.0], data=[normal_data(60)], beta=beta_ladder(2), chains=40, burnin=30,
                         samples=30),
-    # generic models with a lane form: 8 lanes per particle
+    # generic models with a lane form: 8 lanes per particle.  Logistic growth (K3's model): every lane walks the 100-step
+    # map, the 20 Poisson terms are evaluated 8 at a time; 10 rungs = 3 chains per CTA + 2 left-over particle slots
+    "logistic_k3": Case("logistic", [1, 1, 50], [100, 2, 200], data=[POPULATION["pop"], POPULATION["time"]],
+                        beta=beta_ladder(10), chains=5, burnin=40, samples=40),
+    "logistic_times_backwards": Case("logistic", [1, 1, 50], [100, 2, 200],
+                                     data=[POPULATION["pop"][::-1], POPULATION["time"][::-1]], beta=beta_ladder(2), chains=2,
+                                     burnin=15, samples=15),
     "multilevel_g5": multilevel_case(5, 4, 4),
     "multilevel_g50": multilevel_case(50, 3, 16, burnin=10, samples=10),
     "multilevel_g50_r5_hot": multilevel_case(50, 7, 5, burnin=8, samples=8),
@@ -65,7 +71,7 @@ def test_lanes_replay_matches_oracle(name, oracle):
     assert_parity(gpu, ora, RTOL, what=f"[lanes/{name}] ")
 
 
-@pytest.mark.parametrize("name", ["k1_one_chain", "rungs8", "coupling_model", "multilevel_g50"])
+@pytest.mark.parametrize("name", ["k1_one_chain", "rungs8", "coupling_model", "multilevel_g50", "logistic_k3"])
 def test_lanes_philox_matches_oracle(name, oracle):
     case = LANES_CASES[name]
     ora = run_oracle(oracle, case, "philox", seed=99, chain_offset=(1 << 33) + 5)
