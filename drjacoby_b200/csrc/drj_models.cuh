@@ -128,8 +128,11 @@ struct DrjModelMultilevel {
     return ret;
   }
   __device__ static __forceinline__ double logprior(const double*, const DrjList&) { return 0.0; }
-  // lane-split form (drj_lanes.cuh): lane l of 8 adds the terms l, l + 8, ... of the block, in order
-  static constexpr int LANES = 8;
+  // lane-split form (drj_lanes.cuh): lane l of LANES adds the terms l, l + LANES, ... of the block, in order
+#ifndef DRJ_MULTILEVEL_LANES
+#define DRJ_MULTILEVEL_LANES 8  // K4 (4096 x 16, G = 50) measured: 4 lanes 4.6e9 (8 warps per SM: 3 KB of state per particle), 8 lanes 5.2e9, 16 lanes 3.1e9
+#endif
+  static constexpr int LANES = DRJ_MULTILEVEL_LANES;
   __device__ static double loglike_lanes(const double* th, const DrjList& data, const DrjList&, int block, int lane) {
     double ret = 0.0;
     if (block == G + 1) {
