@@ -1644,6 +1644,8 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   a.chains = C; a.rungs = R; a.chains_per_cta = s->cpc; a.team_ctas = s->team_ctas; a.team_stages = team_stages; a.coupling_on = cfg->coupling_on ? 1 : 0;
   a.grid_stages = grid_stages;
   a.grid_slots = (int)std::max<long long>(1, DRJ_NT / std::max<long long>(1, layout_P));  // from the whole run's size: shards stay bit-identical
+  a.grid_tile = (layout_P >= 2 && layout_P <= 8) ? 1 : 0;  // (likewise from the whole run's size)
+  if (const char* e = getenv("DRJ_GRID_TILE")) { if (e[0] == '0') a.grid_tile = 0; else if (e[0] == '1' && layout_P <= 8) a.grid_tile = 1; }
   a.save_hot_draws = cfg->save_hot_draws ? 1 : 0; a.store_pt = cfg->store_pt ? 1 : 0;
   a.rng_mode = cfg->rng_mode; a.d_free = s->d_free;
   a.use_tma = (cfg->flags & DRJ_FLAG_NO_TMA) ? 0 : 1;

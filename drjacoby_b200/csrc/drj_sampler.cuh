@@ -59,6 +59,7 @@ struct DrjKernelArgs {
   int team_stages;     // TEAM kernels: depth of the TMA tile pipeline (tiles resident per CTA), 2..DRJ_TEAM_MAXSTAGES
   int grid_slots;      // GRID kernels: data slots per particle in a CTA (threads slot * P + particle), fixed by the WHOLE run's size
   int grid_stages;     // GRID kernels: depth of the TMA chunk pipeline, 2..DRJ_GRID_MAXSTAGES
+  int grid_tile;       // GRID kernels: 2..8 particles in the WHOLE run: every thread is a data slot and accumulates for all of them
   long long chain_offset;     // global id of chain 0 (Philox counter)
   unsigned long long seed;
   double target_acceptance;
@@ -579,6 +580,50 @@ __device__ __forceinline__ long long drj_grid_first_chunk(long long v, long long
   return (v * nchunks) / nv;
 }
 
+// 2 to 8 particles (the reference's default is five chains): with one thread per (slot, particle) every particle's
+// thread loads the datum again from shared memory -- P loads per datum, and at 5 x 1 the sweep was bound by them (0.80 of
+// the HBM peak, FP64 pipe 36 %, short_scoreboard 1.8).  Here every thread is a slot, loads a 16-byte pair ONCE and
+// accumulates it for all P particles (their Consts and two partial sums each in registers).  Pair p of the item goes to
+// thread p mod 256 (chunks hold a multiple of 256 pairs), its two data to that thread's two sums: the association
+// does not depend on the chunking, the grid size or the launch split.
+#define DRJ_GRID_TILE_MAXP 8
+template <class M, int NP>
+__device__ __forceinline__ void drj_grid_accum_tile_n(const typename M::Consts (&kq)[DRJ_GRID_TILE_MAXP],
+                                                      const double* __restrict__ buf, int cnt, int tid, int nthreads,
+                                                      double (&acc)[DRJ_GRID_TILE_MAXP][2]) {
+  const int np = cnt >> 1;
+  const double2* __restrict__ pq = reinterpret_cast<const double2*>(buf);
+#pragma unroll 4
+  for (int pi = tid; pi < np; pi += nthreads) {
+    const double2 v = pq[pi];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      acc[q][0] = M::datum(kq[q], v.x, acc[q][0]);
+      acc[q][1] = M::datum(kq[q], v.y, acc[q][1]);
+    }
+  }
+  if ((cnt & 1) && tid == np % nthreads) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) acc[q][0] = M::datum(kq[q], buf[cnt - 1], acc[q][0]);
+  }
+}
+// (the particle count as a compile-time constant: predicated-off instructions of absent particles would still issue)
+template <class M>
+__device__ __forceinline__ void drj_grid_accum_tile(const typename M::Consts (&kq)[DRJ_GRID_TILE_MAXP], int P,
+                                                    const double* __restrict__ buf, int cnt, int tid, int nthreads,
+                                                    double (&acc)[DRJ_GRID_TILE_MAXP][2]) {
+  switch (P) {
+    case 1: drj_grid_accum_tile_n<M, 1>(kq, buf, cnt, tid, nthreads, acc); break;
+    case 2: drj_grid_accum_tile_n<M, 2>(kq, buf, cnt, tid, nthreads, acc); break;
+    case 3: drj_grid_accum_tile_n<M, 3>(kq, buf, cnt, tid, nthreads, acc); break;
+    case 4: drj_grid_accum_tile_n<M, 4>(kq, buf, cnt, tid, nthreads, acc); break;
+    case 5: drj_grid_accum_tile_n<M, 5>(kq, buf, cnt, tid, nthreads, acc); break;
+    case 6: drj_grid_accum_tile_n<M, 6>(kq, buf, cnt, tid, nthreads, acc); break;
+    case 7: drj_grid_accum_tile_n<M, 7>(kq, buf, cnt, tid, nthreads, acc); break;
+    default: drj_grid_accum_tile_n<M, 8>(kq, buf, cnt, tid, nthreads, acc); break;
+  }
+}
+
 // Must be called by every thread of every CTA of the grid (uniform control flow).  `own` = index of the particle
 // whose total this thread wants back (its own particle; shadow threads replicate a particle of chain 0).
 template <class M>
@@ -603,6 +648,13 @@ __device__ __forceinline__ double drj_sweep_item_grid(DrjTiles<M, true>& T, cons
   __syncthreads();
   typename M::Consts k;
   if (worker) k = s_consts[q];
+  const bool tile = a.grid_tile != 0 && P <= DRJ_GRID_TILE_MAXP;
+  typename M::Consts kq[DRJ_GRID_TILE_MAXP];
+  if (tile) {
+#pragma unroll
+    for (int qq = 0; qq < DRJ_GRID_TILE_MAXP; ++qq) kq[qq] = s_consts[qq < P ? qq : 0];
+  }
+  __shared__ double s_wsum[DRJ_GRID_TILE_MAXP][DRJ_NT / 32];
 
   const long long nchunks = (n + DRJ_GRID_CHUNK - 1) / DRJ_GRID_CHUNK;
   const long long nv = nchunks < DRJ_GRID_VRANKS ? nchunks : DRJ_GRID_VRANKS;
@@ -640,6 +692,9 @@ __device__ __forceinline__ double drj_sweep_item_grid(DrjTiles<M, true>& T, cons
     const long long c_end = drj_grid_first_chunk(v + 1, nchunks, nv);
     DrjAcc A;
     A.zero();
+    double acc[DRJ_GRID_TILE_MAXP][2];
+#pragma unroll
+    for (int qq = 0; qq < DRJ_GRID_TILE_MAXP; ++qq) { acc[qq][0] = 0.0; acc[qq][1] = 0.0; }
     for (; c < c_end; ++c) {
       const int cnt = (c == nchunks - 1) ? last_cnt : DRJ_GRID_CHUNK;
       if (T.tma) {
@@ -647,7 +702,8 @@ __device__ __forceinline__ double drj_sweep_item_grid(DrjTiles<M, true>& T, cons
         const int cs = T.grid_cs;
         drj_mbar_wait(&full[cs], (T.team_ph >> cs) & 1u);
         T.team_ph ^= 1u << cs;
-        if (worker)
+        if (tile) drj_grid_accum_tile<M>(kq, P, buf + cs * DRJ_GRID_CHUNK, cnt, tid, (int)blockDim.x, acc);
+        else if (worker)
           drj_team_accum<M>(k, buf + cs * DRJ_GRID_CHUNK, cnt, slot, S,
                             cnt == DRJ_GRID_CHUNK ? mine_full : drj_team_pairs(cnt, slot, S), A);
         __syncwarp();
@@ -657,8 +713,28 @@ __device__ __forceinline__ double drj_sweep_item_grid(DrjTiles<M, true>& T, cons
         __syncthreads();
         for (int j = tid; j < cnt; j += blockDim.x) buf[j] = g[c * DRJ_GRID_CHUNK + j];
         __syncthreads();
-        if (worker) drj_team_accum<M>(k, buf, cnt, slot, S, cnt == DRJ_GRID_CHUNK ? mine_full : drj_team_pairs(cnt, slot, S), A);
+        if (tile) drj_grid_accum_tile<M>(kq, P, buf, cnt, tid, (int)blockDim.x, acc);
+        else if (worker) drj_team_accum<M>(k, buf, cnt, slot, S, cnt == DRJ_GRID_CHUNK ? mine_full : drj_team_pairs(cnt, slot, S), A);
       }
+    }
+    if (tile) {
+      // per particle: the 32 slot sums of a warp by an xor-shuffle tree, the warps' sums in order
+#pragma unroll
+      for (int qq = 0; qq < DRJ_GRID_TILE_MAXP; ++qq)
+        if (qq < P) {
+          double t = acc[qq][0] + acc[qq][1];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+          if (lane == 0) s_wsum[qq][tid >> 5] = t;
+        }
+      __syncthreads();
+      if (tid < P) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_wsum[tid][w];
+        part[v * P + tid] = t;
+      }
+      __syncthreads();  // (s_wsum is rewritten by the next virtual rank)
+      continue;
     }
     // the S slot sums of every particle, fixed two-level order: group j takes slots j, j + J, ... in sequence,
     // then the J group sums in sequence

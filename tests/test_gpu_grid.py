@@ -46,6 +46,12 @@ GRID_CASES = {
                      burnin=5, samples=5),
     # more chunks (1221) than virtual ranks (1184): ranks of one and two chunks
     "many_chunks": Case("normal_mu", [-np.inf], [np.inf], data=[normal_data(10_000_001)], chains=2, burnin=3, samples=3),
+    # 2..8 particles in the whole run: the tile form (every thread a data slot, all particles' sums in registers);
+    # the reference's default of five single-rung chains, odd length (a lone last datum), ragged last chunk
+    "tile_five": Case("example", [-10, 0], [10, np.inf], data=[normal_data(50_003)], chains=5, burnin=12, samples=12),
+    # eight particles (the most the tile form takes) with coupling, fewer data pairs (150) than threads
+    "tile_eight": Case("coupling", [-10, 0, -np.inf], [10, 10, np.inf], data=[normal_data(301, 4, 10.0, 1.0)],
+                       beta=beta_ladder(4), chains=2, burnin=15, samples=15),
 }
 
 
@@ -97,7 +103,7 @@ def test_grid_is_the_default_for_few_particles_over_very_long_data():
         assert differs, "the kernel families associate the sum differently; identical bits mean a flag was ignored"
 
 
-@pytest.mark.parametrize("name", ["one_chain", "coupling_r20", "many_chunks"])
+@pytest.mark.parametrize("name", ["one_chain", "coupling_r20", "many_chunks", "tile_five"])
 def test_grid_result_does_not_depend_on_grid_size_or_pipeline_depth(name):
     case = GRID_CASES[name]
     ref = run_gpu(case, "philox", seed=8, flags=F().FLAG_GRID_KERNEL)
@@ -108,6 +114,32 @@ def test_grid_result_does_not_depend_on_grid_size_or_pipeline_depth(name):
     finally:
         os.environ.pop("DRJ_GRID_CTAS", None)
         os.environ.pop("DRJ_GRID_STAGES", None)
+
+
+@pytest.mark.parametrize("name", ["tile_five", "tile_eight", "stream_r2"])
+def test_grid_tile_form_agrees_with_the_slot_form(name):
+    """2..8 particles take the tile form by default (DRJ_GRID_TILE=0 turns it off): it associates the sum differently
+    from one thread per (slot, particle), so the two agree within the gate, bit for bit in every count, and not in
+    every last bit; with and without TMA the tile form gives the same bits."""
+    case = GRID_CASES[name]
+    tile = run_gpu(case, "philox", seed=5, flags=F().FLAG_GRID_KERNEL)
+    same_bits(tile, run_gpu(case, "philox", seed=5, flags=F().FLAG_GRID_KERNEL | F().FLAG_NO_TMA), "tile: TMA vs plain")
+    try:
+        os.environ["DRJ_GRID_TILE"] = "0"
+        slot = run_gpu(case, "philox", seed=5, flags=F().FLAG_GRID_KERNEL)
+    finally:
+        os.environ.pop("DRJ_GRID_TILE", None)
+    differs = False
+    for k in tile:
+        if k == "t_diff":
+            continue
+        if tile[k].dtype.kind == "f":
+            ok, worst = rel_close(tile[k], slot[k], rtol=RTOL)
+            assert ok, (k, worst)
+            differs = differs or not np.array_equal(tile[k], slot[k])
+        else:
+            assert np.array_equal(tile[k], slot[k]), k
+    assert differs, "identical bits: DRJ_GRID_TILE was ignored"
 
 
 def test_grid_tma_and_plain_staging_agree():
@@ -131,6 +163,17 @@ def test_grid_launch_split_and_sharding_are_bitwise_invariant():
     for k in full:
         if k != "t_diff":
             assert np.array_equal(part[k], full[k][lo:hi]), k
+    # the tile form: a one-chain shard of the five-chain run (the layout, and with it the form, follows the WHOLE run)
+    case = GRID_CASES["tile_five"]
+    full = run_gpu(case, "philox", seed=21, flags=F().FLAG_GRID_KERNEL)
+    same_bits(full, run_gpu(case, "philox", seed=21, flags=F().FLAG_GRID_KERNEL, iters_per_launch=5))
+    for lo, hi in ((2, 3), (3, 5)):
+        shard = Case(case.model, case.tmin, case.tmax, data=case.data, beta=case.beta, chains=hi - lo, burnin=case.burnin,
+                     samples=case.samples, init=case.init[lo:hi])
+        part = run_gpu(shard, "philox", seed=21, chain_offset=lo, flags=F().FLAG_GRID_KERNEL, layout_chains=case.chains)
+        for k in full:
+            if k != "t_diff":
+                assert np.array_equal(part[k], full[k][lo:hi]), (k, lo, hi)
 
 
 def test_grid_small_and_empty_data(oracle):
