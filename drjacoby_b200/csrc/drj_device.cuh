@@ -255,6 +255,19 @@ __device__ __forceinline__ double dlnorm(double x, double meanlog, double sdlog,
             : 0.398942280401432677939946059934 * exp(-0.5 * y * y) / (x * sdlog);
 }
 
+// dlnorm with log(x) supplied by the caller (bit for bit the value log(x) would give: the sampler's cached
+// Jacobian logarithm of a parameter whose lower bound is 0, see DrjHints)
+__device__ __forceinline__ double dlnorm_l(double x, double logx, double meanlog, double sdlog, int lg) {
+  if (isnan(x) || isnan(meanlog) || isnan(sdlog)) return x + meanlog + sdlog;
+  if (sdlog < 0) return DRJ_NAN;
+  if (!isfinite(x) && logx == meanlog) return DRJ_NAN;
+  if (sdlog == 0) return (logx == meanlog) ? DRJ_INF : drj_nmath::d0(lg);
+  if (x <= 0) return drj_nmath::d0(lg);
+  double y = (logx - meanlog) / sdlog;
+  return lg ? -(DRJ_LN_SQRT_2PI + 0.5 * y * y + (sdlog == 1.0 ? logx : log(x * sdlog)))
+            : 0.398942280401432677939946059934 * exp(-0.5 * y * y) / (x * sdlog);
+}
+
 __device__ inline double dpois(double x, double lambda, int lg) {
   if (isnan(x) || isnan(lambda)) return x + lambda;
   if (lambda < 0) return DRJ_NAN;

@@ -1645,6 +1645,17 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   a.grid_stages = grid_stages;
   a.grid_slots = (int)std::max<long long>(1, DRJ_NT / std::max<long long>(1, layout_P));  // from the whole run's size: shards stay bit-identical
   a.grid_tile = (layout_P >= 2 && layout_P <= 8) ? 1 : 0;  // (likewise from the whole run's size)
+  {
+    bool trivial = model->NBLOCK == 1;
+    for (int i = 0; i < D && trivial; ++i)
+      if (!cfg->skip_param[i]) trivial = cfg->block_ptr[i + 1] - cfg->block_ptr[i] == 1 && cfg->block_idx[cfg->block_ptr[i]] == 1;
+    a.blocks_trivial = trivial ? 1 : 0;
+    unsigned m = 0u;
+    for (int i = 0; i < D && i < 32; ++i)
+      if ((cfg->trans_type[i] == 2 || cfg->trans_type[i] == 3) && cfg->theta_min[i] == 0.0) m |= 1u << i;
+    if (const char* e = getenv("DRJ_NO_HINTS")) if (e[0] == '1') m = 0u;
+    a.lo_is_log = m;
+  }
   if (const char* e = getenv("DRJ_GRID_TILE")) { if (e[0] == '0') a.grid_tile = 0; else if (e[0] == '1' && layout_P <= 8) a.grid_tile = 1; }
   a.save_hot_draws = cfg->save_hot_draws ? 1 : 0; a.store_pt = cfg->store_pt ? 1 : 0;
   a.rng_mode = cfg->rng_mode; a.d_free = s->d_free;

@@ -17,12 +17,16 @@
 struct DrjNormConsts {
   double mean, half_inv_var, lognorm;
 };
-__device__ __forceinline__ bool drj_norm_prepare(double mean, double sd, DrjNormConsts& k) {
+__device__ __forceinline__ bool drj_norm_prepare_l(double mean, double sd, double logsd, DrjNormConsts& k) {
   k.mean = mean;
   k.half_inv_var = 0.5 / (sd * sd);
-  k.lognorm = DRJ_LN_SQRT_2PI + log(sd);
+  k.lognorm = DRJ_LN_SQRT_2PI + logsd;
   // outside this range R::dnorm's edge-case branches matter: use the exact serial evaluation
   return (sd > 1e-150) && (sd < 1e150) && (fabs(mean) < 1e150);
+}
+__device__ __forceinline__ bool drj_norm_prepare(double mean, double sd, DrjNormConsts& k) {
+  // (log(1) is exactly +0: where sd is the literal 1 the compiler drops the logarithm, which it cannot fold itself)
+  return drj_norm_prepare_l(mean, sd, sd == 1.0 ? 0.0 : log(sd), k);
 }
 __device__ __forceinline__ double drj_norm_datum(const DrjNormConsts& k, double x, double acc) {
   const double d = x - k.mean;
@@ -52,7 +56,15 @@ struct DrjModelExample {
     return drj_norm_serial(data.item(0), data.len(0), th[0], th[1]);
   }
   __device__ static __forceinline__ double logprior(const double* th, const DrjList&) {
-    return -log(20.0) + R::dlnorm(th[1], 0.0, 1.0, 1);
+    return -2.99573227355399099343 + R::dlnorm(th[1], 0.0, 1.0, 1);
+  }
+  // sigma's lower bound is 0 in the reference's parameter table: log(sigma) is the sampler's Jacobian logarithm (DrjHints)
+  static constexpr bool HINTS = true;
+  __device__ static __forceinline__ bool prepare_h(const double* th, const DrjList&, int, Consts& k, const double* loglo, unsigned mask) {
+    return drj_norm_prepare_l(th[0], th[1], (mask & 2u) ? loglo[1] : log(th[1]), k);
+  }
+  __device__ static __forceinline__ double logprior_h(const double* th, const DrjList&, const double* loglo, unsigned mask) {
+    return -2.99573227355399099343 + ((mask & 2u) ? R::dlnorm_l(th[1], loglo[1], 0.0, 1.0, 1) : R::dlnorm(th[1], 0.0, 1.0, 1));
   }
 };
 
@@ -76,7 +88,7 @@ struct DrjModelCoupling {
     return drj_norm_serial(data.item(0), data.len(0), th[0] * th[0] * th[1] + th[2], 1.0);
   }
   __device__ static __forceinline__ double logprior(const double* th, const DrjList&) {
-    return -log(20.0) - log(10.0) + R::dnorm(th[2], 0.0, 1.0, 1);
+    return -2.99573227355399099343 - 2.30258509299404568402 + R::dnorm(th[2], 0.0, 1.0, 1);
   }
 };
 

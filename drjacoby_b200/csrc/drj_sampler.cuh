@@ -59,6 +59,9 @@ struct DrjKernelArgs {
   int team_stages;     // TEAM kernels: depth of the TMA tile pipeline (tiles resident per CTA), 2..DRJ_TEAM_MAXSTAGES
   int grid_slots;      // GRID kernels: data slots per particle in a CTA (threads slot * P + particle), fixed by the WHOLE run's size
   int grid_stages;     // GRID kernels: depth of the TMA chunk pipeline, 2..DRJ_GRID_MAXSTAGES
+  int blocks_trivial;  // a one-block model whose every free parameter lists exactly that block: no block lists are read
+  unsigned lo_is_log;  // bit i: parameter i (< 32) has a lower bound of exactly 0, so its cached Jacobian logarithm
+                       // log(theta_i - min_i) IS log(theta_i) (models with HINTS reuse it instead of taking the logarithm again)
   int grid_tile;       // GRID kernels: 2..8 particles in the WHOLE run: every thread is a data slot and accumulates for all of them
   long long chain_offset;     // global id of chain 0 (Philox counter)
   unsigned long long seed;
@@ -773,11 +776,37 @@ __device__ __forceinline__ double drj_sweep_item_grid(DrjTiles<M, true>& T, cons
   return tot;
 }
 
+// Optional model hook (HINTS): the sampler already holds log(theta_i - min_i) of every parameter with a lower bound (the
+// Jacobian term of the reparameterisation, Particle.cpp:100-118); where min_i is exactly 0 that IS log(theta_i), the value
+// a scale parameter's likelihood (log sd) and a log-normal or gamma prior (log x) compute again -- the n = 100 normal
+// model took log(sigma) three times per sigma update.  A model with `static constexpr bool HINTS = true` provides
+//   prepare_h(theta, misc, block, k, loglo, mask)   [per-datum models]   and   logprior_h(theta, misc, loglo, mask)
+// and may use loglo[i] for log(theta[i]) when bit i of mask is set: the same function of the same argument, so the
+// same bits.
+template <class M, class = void>
+struct DrjHints {
+  template <class K>  // (K = M::Consts; a template so that models without a per-datum form can instantiate the class)
+  __device__ static __forceinline__ bool prepare(const double* th, const DrjList& misc, int block, K& k,
+                                                 const double*, unsigned) { return M::prepare(th, misc, block, k); }
+  __device__ static __forceinline__ double logprior(const double* th, const DrjList& misc, const double*, unsigned) {
+    return M::logprior(th, misc);
+  }
+};
+template <class M>
+struct DrjHints<M, decltype((void)M::HINTS)> {
+  template <class K>
+  __device__ static __forceinline__ bool prepare(const double* th, const DrjList& misc, int block, K& k,
+                                                 const double* loglo, unsigned mask) { return M::prepare_h(th, misc, block, k, loglo, mask); }
+  __device__ static __forceinline__ double logprior(const double* th, const DrjList& misc, const double* loglo, unsigned mask) {
+    return M::logprior_h(th, misc, loglo, mask);
+  }
+};
+
 template <class M, int MODE>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const DrjKernelArgs& a,
-                                                   const double* theta, int block, int own) {
+                                                   const double* theta, int block, int own, const double* loglo = nullptr) {
   typename M::Consts k;
-  const bool fast = M::prepare(theta, a.misc, block, k);
+  const bool fast = DrjHints<M>::prepare(theta, a.misc, block, k, loglo, loglo ? a.lo_is_log : 0u);
   const int item = M::datum_item(block);
   const long long n = a.data.len(item);
   double acc;  // uniform: all threads sweep
@@ -790,7 +819,7 @@ __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const D
 
 template <class M, int MODE>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, false>&, const DrjKernelArgs& a,
-                                                   const double* theta, int block, int) {
+                                                   const double* theta, int block, int, const double* = nullptr) {
   return M::loglike(theta, a.data, a.misc, block);
 }
 
@@ -1061,6 +1090,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   const bool do_couple = a.coupling_on && R > 1;
   const bool wl = MODE == DRJ_MODE_SOLO && a.warp_local != 0;
   const int lane = tid & 31;
+  const bool bt = B == 1 && a.blocks_trivial != 0;  // (no reads of the block lists: they were 5 % of the n = 100 sweep's instructions)
 
   for (int it = 0; it < a.n_iter; ++it) {
     const int t = a.iter0 + it;  // global update index, 1-based
@@ -1098,14 +1128,16 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           adj = hi_p + lo_p - s.ahi[i] - s.alo[i];
         } break;
       }
-      const double th_cur = s.theta[i];
-      s.theta[i] = th_p;  // s.theta is theta_prop from here to the accept/reject
+      const double th_cur = s.theta[i], alo_cur = s.alo[i];
+      s.theta[i] = th_p;  // s.theta is theta_prop (and s.alo its Jacobian logarithms) from here to the accept/reject
+      s.alo[i] = lo_p;
       // likelihood of the blocks this parameter belongs to (Particle.h:107-112)
-      for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
-        const int b = a.block_idx[j];
+      const int jb = bt ? 0 : a.block_ptr[i], je = bt ? 1 : a.block_ptr[i + 1];
+      for (int j = jb; j < je; ++j) {
+        const int b = bt ? 1 : a.block_idx[j];
         if constexpr (STREAM) {
           typename M::Consts k;
-          const bool fast = M::prepare(s.theta, a.misc, b, k);
+          const bool fast = DrjHints<M>::prepare(s.theta, a.misc, b, k, s.alo, a.lo_is_log);
           const int item = M::datum_item(b);
           const long long n = a.data.len(item);
           if (active) drj_store_state<M>(a, s, p);                          // park (theta slot i holds theta')
@@ -1113,13 +1145,13 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           drj_load_state<M>(a, s, p);
           s.llb_p[B == 1 ? 0 : b - 1] = fast ? M::finish(k, acc, n) : M::loglike(s.theta, a.data, a.misc, b);
         } else {
-          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, MODE>(T, a, s.theta, b, (int)p);
+          s.llb_p[B == 1 ? 0 : b - 1] = drj_eval_loglike<M, MODE>(T, a, s.theta, b, (int)p, s.alo);
         }
       }
       double ll_p = 0.0;
 #pragma unroll UB
       for (int b = 0; b < B; ++b) ll_p += s.llb_p[b];  // sequential, index order (misc.h:20-27)
-      const double lp_p = M::logprior(s.theta, a.misc);
+      const double lp_p = DrjHints<M>::logprior(s.theta, a.misc, s.alo, a.lo_is_log);
       // NaN / +Inf guard (Particle.h:121-128)
       if (err == 0 && valid) {
         if (isnan(ll_p) || ll_p == DRJ_INF) err = DRJ_ERR_LOGLIKE_BAD;
@@ -1138,8 +1170,8 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       // divergent branch here made every warp run both sides (n = 100 sweep: 26.7 of 32 lanes active, round 1)
 #ifdef DRJ_ACCEPT_BRANCH
       if (accept) {
-        s.phi[i] = phi_p; s.alo[i] = lo_p; s.ahi[i] = hi_p;
-        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+        s.phi[i] = phi_p; s.ahi[i] = hi_p;
+        for (int j = jb; j < je; ++j) {
           const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
           s.llb[b] = s.llb_p[b];
         }
@@ -1147,8 +1179,8 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         s.logbw[i] = fma(1.0 - target, gain, s.logbw[i]);
         s.acc++;
       } else {
-        s.theta[i] = th_cur;
-        for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+        s.theta[i] = th_cur; s.alo[i] = alo_cur;
+        for (int j = jb; j < je; ++j) {
           const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
           s.llb_p[b] = s.llb[b];
         }
@@ -1157,10 +1189,10 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       s.bwi[i]++;
 #else
       s.phi[i] = accept ? phi_p : s.phi[i];
-      s.alo[i] = accept ? lo_p : s.alo[i];
+      s.alo[i] = accept ? lo_p : alo_cur;
       s.ahi[i] = accept ? hi_p : s.ahi[i];
       s.theta[i] = accept ? th_p : th_cur;
-      for (int j = a.block_ptr[i]; j < a.block_ptr[i + 1]; ++j) {
+      for (int j = jb; j < je; ++j) {
         const int b = (B == 1) ? 0 : a.block_idx[j] - 1;
         const double v = accept ? s.llb_p[b] : s.llb[b];
         s.llb[b] = v;

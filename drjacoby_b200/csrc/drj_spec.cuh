@@ -204,23 +204,23 @@ __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
       const double alo_cur = a0 < 0 ? drj_pick<D>(alo, ik) : t_lo[a0], ahi_cur = a0 < 0 ? drj_pick<D>(ahi, ik) : t_hi[a0];
       adj = (tt == 0) ? 0.0 : (tt == 1) ? (hi_p - ahi_cur) : (tt == 2) ? (lo_p - alo_cur) : (hi_p + lo_p - ahi_cur - alo_cur);
     }
-    double thn[D];
+    double thn[D], lon[D];  // (lon: the Jacobian logarithms log(theta_i - min_i) that go with thn, for models with HINTS)
 #pragma unroll
-    for (int i = 0; i < D; ++i) thn[i] = (i == ik) ? th_p : theta[i];
+    for (int i = 0; i < D; ++i) { thn[i] = (i == ik) ? th_p : theta[i]; lon[i] = (i == ik) ? lo_p : alo[i]; }
 #pragma unroll
     for (int dl = 1; dl < D; ++dl) {
       const int src = anc[dl];
       if (dl < F && src >= 0) {
-        const double pt = t_th[src];
+        const double pt = t_th[src], pl = t_lo[src];
         const int fo = fk - dl + (fk < dl ? F : 0);  // the free slot `dl` updates before this node's
         const int io = s_fl[fo];
 #pragma unroll
-        for (int i = 0; i < D; ++i) thn[i] = (i == io) ? pt : thn[i];
+        for (int i = 0; i < D; ++i) { thn[i] = (i == io) ? pt : thn[i]; lon[i] = (i == io) ? pl : lon[i]; }
       }
     }
     // likelihood and prior at theta' (Particle.h:107-118), the one-thread-per-particle evaluation
-    const double ll_p = drj_eval_loglike<M, DRJ_MODE_SOLO>(T, a, thn, 1, 0);
-    const double lp_p = M::logprior(thn, a.misc);
+    const double ll_p = drj_eval_loglike<M, DRJ_MODE_SOLO>(T, a, thn, 1, 0, lon);
+    const double lp_p = DrjHints<M>::logprior(thn, a.misc, lon, a.lo_is_log);
 
     // ================= the decisions =================
     // Every node takes ITS OWN decision at once, assuming its path: the current log-likelihood / log-prior on the path
