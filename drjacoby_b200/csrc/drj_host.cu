@@ -302,6 +302,55 @@ __global__ void __launch_bounds__(256) drj_quantile_hist(const double* __restric
     if (qh[i]) atomicAdd(&hist[(long long)g0 * DRJ_QBINS + i], (unsigned long long)qh[i]);
 }
 
+// The state-independent part of every update of one launch, for runs too small to fill the machine: in such a run every
+// thread is one dependent chain of ~1000 instructions per update, a third of them the counter-based draw (Philox, the
+// inverse normal, log u) that does not depend on the chain at all.  This kernel computes them for all iterations of
+// the launch at once with the whole GPU (same device functions, same bits), the sweep kernel reads them back.
+// Element (it, free slot, particle) of z / lu at ((it * d_free + slot) * P + p); coupling log u at
+// ((it * chains + chain) * (R - 1) + pair).  Counters as in the sweep kernel (drj_sampler.cuh).
+__global__ void __launch_bounds__(256) drj_draw_kernel(const DrjKernelArgs a, double* __restrict__ z, double* __restrict__ lu,
+                                                        double* __restrict__ clu, const int* __restrict__ free_param) {
+  const long long P = a.P;
+  const int R = a.rungs, DF = a.d_free;
+  const unsigned k0 = (unsigned)a.seed, k1 = (unsigned)(a.seed >> 32);
+  const long long per_it = P * DF, total = per_it * a.n_iter;
+  const long long stride = (long long)gridDim.x * blockDim.x, first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long e = first; e < total; e += stride) {
+    const long long it = e / per_it, rem = e - it * per_it;
+    const int fs = (int)(rem / P);
+    const long long p = rem - (long long)fs * P, chain = p / R;
+    const int r = (int)(p - chain * R);
+    const int t = a.iter0 + (int)it;
+    double u1, u2, u3;
+    if (a.rng_mode) {
+      const double* q = a.replay + (chain * a.replay_T + (t - 1)) * a.replay_U + 3 * ((long long)r * DF + fs);
+      u1 = q[0]; u2 = q[1]; u3 = q[2];
+    } else {
+      const unsigned long long g = (unsigned long long)(a.chain_offset + chain);
+      DrjU4 w = drj_philox4x32_10((unsigned)g, (unsigned)t, ((unsigned)r << 16) | (unsigned)free_param[fs], (unsigned)(g >> 32) << 8, k0, k1);
+      u1 = drj_u32_to_unif(w.x); u2 = drj_u32_to_unif(w.y); u3 = drj_u32_to_unif(w.z);
+    }
+    z[e] = drj_norm_rand(u1, u2);
+    lu[e] = log(u3);
+  }
+  if (clu && R > 1) {
+    const long long per_it2 = a.chains * (R - 1), total2 = per_it2 * a.n_iter;
+    for (long long e = first; e < total2; e += stride) {
+      const long long it = e / per_it2, rem = e - it * per_it2, chain = rem / (R - 1);
+      const int r = (int)(rem - chain * (R - 1));
+      const int t = a.iter0 + (int)it;
+      double u;
+      if (a.rng_mode) u = a.replay[(chain * a.replay_T + (t - 1)) * a.replay_U + 3LL * DF * R + r];
+      else {
+        const unsigned long long g = (unsigned long long)(a.chain_offset + chain);
+        DrjU4 w = drj_philox4x32_10((unsigned)g, (unsigned)t, (unsigned)r, 1u | ((unsigned)(g >> 32) << 8), k0, k1);
+        u = drj_u32_to_unif(w.x);
+      }
+      clu[e] = log(u);
+    }
+  }
+}
+
 // FP64 FMA throughput probe: 8 independent dependent-chains per thread
 __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
@@ -932,6 +981,8 @@ struct drj_session {
   unsigned long long* err_key = nullptr;
   int64_t sweep_launches = 0, aux_launches = 0;
   bool stream_variant = false;  // data too large for shared memory: use the streaming sweep kernel
+  double *draw_z = nullptr, *draw_lu = nullptr, *draw_clu = nullptr;  // draws computed ahead (DrjKernelArgs::draws)
+  int* d_free_param = nullptr;  // free slot -> parameter index
   bool team = false;            // few chains x long data: cluster-per-chain kernels (drj_sweep_item_team)
   int team_ctas = 1;            // CTAs per cluster
   bool team_ctas_forced = false;
@@ -1043,6 +1094,13 @@ static int launch_init_chain(drj_session* s, drj_error* err) {
 static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
   const drj_model* m = s->model;
   void* params[] = {(void*)&s->a};
+  if (sweep && s->a.draws) {  // the draws of this launch's iterations, ahead of the sweep on the same stream
+    const long long work = s->P * s->d_free * (long long)s->a.n_iter;
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 8LL * 148);
+    drj_draw_kernel<<<std::max(1, blocks), 256, 0, s->stream>>>(s->a, s->draw_z, s->draw_lu, s->draw_clu, s->d_free_param);
+    CUDA_TRY(cudaGetLastError());
+    s->aux_launches++;
+  }
   const bool stream = sweep && s->stream_variant;
   if (s->gridk) {  // the whole grid is one team: cooperative launch (all CTAs co-resident), barrier counter at 0
     CUDA_TRY(cudaMemsetAsync(s->grid_bar, 0, sizeof(unsigned int), s->stream));
@@ -1666,6 +1724,31 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
   CUDA_TRY(upload(s, &a.theta_max, cfg->theta_max, D));
   CUDA_TRY(upload(s, &a.trans_type, cfg->trans_type, D));
   CUDA_TRY(upload(s, &a.free_slot, free_slot.data(), D));
+  std::vector<int> free_param;
+  for (int i = 0; i < D; ++i) if (free_slot[i] >= 0) free_param.push_back(i);
+  {
+    // draws computed ahead for the one-thread-per-particle kernels when the run is too small to fill the machine (at
+    // most two warps per scheduler: every update is then pure latency, and the draw is a third of it); from ~2 warps per
+    // scheduler on the sweep hides that latency itself and the extra pass through HBM would only cost
+    cudaDeviceProp prop3;
+    const bool solo = !s->team && !s->gridk && !s->lanes && !s->spec;
+    const double draw_bytes = 16.0 * ((double)s->tb + 1) * s->d_free * (double)P + 8.0 * (double)s->tb * (double)C * std::max(R - 1, 1);
+    bool want = solo && s->d_free > 0 && device_props(cfg->device, &prop3) == cudaSuccess &&
+                P <= 32LL * 8 * prop3.multiProcessorCount && draw_bytes <= 1.0e9;
+    if (const char* e = getenv("DRJ_DRAWS")) want = (e[0] == '1') ? (solo && s->d_free > 0 && draw_bytes <= 8.0e9) : (e[0] == '0' ? false : want);
+    if (want) {
+      const size_t rows = ((size_t)s->tb + 1) * (size_t)s->d_free * (size_t)P;
+      CUDA_TRY(dalloc(s, &s->draw_z, rows));
+      CUDA_TRY(dalloc(s, &s->draw_lu, rows));
+      CUDA_TRY(cudaMemsetAsync(s->draw_z, 0, rows * sizeof(double), s->stream));   // (the padded row is read, never used)
+      CUDA_TRY(cudaMemsetAsync(s->draw_lu, 0, rows * sizeof(double), s->stream));
+      if (cfg->coupling_on && R > 1) CUDA_TRY(dalloc(s, &s->draw_clu, (size_t)s->tb * (size_t)C * (size_t)(R - 1)));
+      const int* fp = nullptr;
+      CUDA_TRY(upload(s, &fp, free_param.data(), free_param.size()));
+      s->d_free_param = const_cast<int*>(fp);
+      a.draws = 1; a.draw_z = s->draw_z; a.draw_lu = s->draw_lu; a.draw_clu = s->draw_clu;
+    }
+  }
   CUDA_TRY(upload(s, &a.block_ptr, cfg->block_ptr, D + 1));
   CUDA_TRY(upload(s, &a.block_idx, cfg->block_idx, cfg->block_ptr[D]));
   CUDA_TRY(upload(s, &a.beta_raised, cfg->beta_raised, R));

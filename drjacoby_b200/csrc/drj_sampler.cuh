@@ -59,6 +59,12 @@ struct DrjKernelArgs {
   int team_stages;     // TEAM kernels: depth of the TMA tile pipeline (tiles resident per CTA), 2..DRJ_TEAM_MAXSTAGES
   int grid_slots;      // GRID kernels: data slots per particle in a CTA (threads slot * P + particle), fixed by the WHOLE run's size
   int grid_stages;     // GRID kernels: depth of the TMA chunk pipeline, 2..DRJ_GRID_MAXSTAGES
+  int draws;           // one-thread-per-particle kernels: the state-independent part of every update of this launch (the standard
+                       // normal draw and log u of the accept test, log u of every coupling pair) was computed by
+                       // drj_draw_kernel into draw_z / draw_lu / draw_clu (runs too small to fill the machine)
+  const double* draw_z;    // [n_iter + 1][d_free][P]  (one padded row: the loads run one update ahead)
+  const double* draw_lu;   // same layout
+  const double* draw_clu;  // [n_iter][chains][rungs - 1]
   int blocks_trivial;  // a one-block model whose every free parameter lists exactly that block: no block lists are read
   unsigned lo_is_log;  // bit i: parameter i (< 32) has a lower bound of exactly 0, so its cached Jacobian logarithm
                        // log(theta_i - min_i) IS log(theta_i) (models with HINTS reuse it instead of taking the logarithm again)
@@ -1092,10 +1098,19 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   const int lane = tid & 31;
   const bool bt = B == 1 && a.blocks_trivial != 0;  // (no reads of the block lists: they were 5 % of the n = 100 sweep's instructions)
 
+  // draws computed ahead (a.draws): element (it, free slot, particle) at ((it * d_free + slot) * P + p), so consecutive
+  // updates of this thread are P apart; the loads run one update ahead of their use
+  const bool draws = MODE == DRJ_MODE_SOLO && a.draws != 0;
+  long long de = p;
+  double z_nx = 0.0, lu_nx = 0.0;
+  if (draws) { z_nx = a.draw_z[de]; lu_nx = a.draw_lu[de]; }
+
   for (int it = 0; it < a.n_iter; ++it) {
     const int t = a.iter0 + it;  // global update index, 1-based
     int err = 0;
     const double* rp = a.rng_mode ? a.replay + (cc * a.replay_T + (t - 1)) * a.replay_U : nullptr;
+    double clu = 0.0;
+    if (draws && do_couple && r < R - 1) clu = a.draw_clu[((long long)it * a.chains + cc) * (R - 1) + r];
 
     // ================= Particle::update =================
     constexpr int UP = (D <= 8) ? D : 1;  // the update body itself is only unrolled for small d
@@ -1103,17 +1118,26 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
     for (int i = 0; i < D; ++i) {
       const int fs = s_free[i];
       if (fs < 0) continue;  // skip_param: no RNG consumed (Particle.h:91-93)
-      double u1, u2, u3;
-      if (a.rng_mode) {
-        const double* q = rp + 3 * ((long long)r * a.d_free + fs);
-        u1 = q[0]; u2 = q[1]; u3 = q[2];
+      double zq, lu3;  // the standard normal draw of the proposal, log u of the accept test
+      if (draws) {
+        zq = z_nx; lu3 = lu_nx;
+        de += P;
+        z_nx = a.draw_z[de]; lu_nx = a.draw_lu[de];
       } else {
-        DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, ((unsigned)r << 16) | (unsigned)i, gchain_hi << 8, k0, k1);
-        u1 = drj_u32_to_unif(w.x); u2 = drj_u32_to_unif(w.y); u3 = drj_u32_to_unif(w.z);
+        double u1, u2, u3;
+        if (a.rng_mode) {
+          const double* q = rp + 3 * ((long long)r * a.d_free + fs);
+          u1 = q[0]; u2 = q[1]; u3 = q[2];
+        } else {
+          DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, ((unsigned)r << 16) | (unsigned)i, gchain_hi << 8, k0, k1);
+          u1 = drj_u32_to_unif(w.x); u2 = drj_u32_to_unif(w.y); u3 = drj_u32_to_unif(w.z);
+        }
+        zq = drj_norm_rand(u1, u2);
+        lu3 = log(u3);
       }
       // propose_phi
       const double bw = exp(s.logbw[i]);
-      const double phi_p = drj_rnorm(s.phi[i], bw, u1, u2);
+      const double phi_p = drj_rnorm_from(s.phi[i], bw, zq);
       // phi_prop_to_theta_prop + get_adjustment
       const double tmin = s_tmin[i], tmax = s_tmax[i];
       double th_p, lo_p = 0.0, hi_p = 0.0, adj = 0.0;
@@ -1164,7 +1188,7 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       double MH;
       if (beta == 0.0) MH = __dadd_rn(lp_p - s.lp, adj);
       else MH = __dadd_rn(__dadd_rn(__dmul_rn(beta, ll_p - s.ll), lp_p - s.lp), adj);
-      const bool accept = (log(u3) < MH) && (err == 0);
+      const bool accept = (lu3 < MH) && (err == 0);
       const double gain = rsqrt((double)s.bwi[i]);  // bw_stepsize = 1
       // accept / reject as selects, not as a branch: the lanes of a warp decide differently at every update, and a
       // divergent branch here made every warp run both sides (n = 100 sweep: 26.7 of 32 lanes active, round 1)
@@ -1238,13 +1262,16 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
         }
       }
       if (r < R - 1 && (!TEAM || tid < R)) {
-        double u;
-        if (a.rng_mode) u = rp[3LL * a.d_free * R + r];
+        if (draws) s_logu[tid] = clu;
         else {
-          DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, (unsigned)r, 1u | (gchain_hi << 8), k0, k1);
-          u = drj_u32_to_unif(w.x);
+          double u;
+          if (a.rng_mode) u = rp[3LL * a.d_free * R + r];
+          else {
+            DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, (unsigned)r, 1u | (gchain_hi << 8), k0, k1);
+            u = drj_u32_to_unif(w.x);
+          }
+          s_logu[tid] = log(u);
         }
-        s_logu[tid] = log(u);
       }
       drj_sync(wl);
       // sequential part hot -> cold (the swap of pair i sees the outcome of pair i-1: the replica that moves up carries

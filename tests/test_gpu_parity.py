@@ -5,6 +5,8 @@ gate = BASELINE.json's: log-likelihoods / states within 1e-10 relative, acceptan
 counts bit-exact.  Philox mode: the oracle implements the same counter layout, so the same gate
 applies to the production RNG path.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -138,6 +140,52 @@ def test_stream_tma_and_plain_staging_agree():
     for k in a:
         if k != "t_diff":
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("mode", ["philox", "replay"])
+@pytest.mark.parametrize("name", ["example_rungs4", "doublewell_k2", "example_rungs33", "example_coupling_off", "example_stream",
+                                  "logistic_k3", "multilevel_g5"])
+def test_draws_computed_ahead_are_the_same_draws(name, mode, monkeypatch):
+    """A run too small to fill the machine (every case of this file) has the state-independent part of its updates -- the
+    standard normal draw, log u of the accept test, log u of every coupling pair -- computed ahead by drj_draw_kernel
+    (DESIGN 4); DRJ_DRAWS=0 makes every thread draw for itself, as the large runs do.  Same functions of the same
+    counters: same bits, whatever the launch split."""
+    case = CASES[name]
+    from drjacoby_b200 import _lib
+    kw = dict(flags=_lib.FLAG_NO_LANES_KERNEL | _lib.FLAG_NO_SPEC_KERNEL | _lib.FLAG_NO_TEAM_KERNEL)
+    if mode == "replay":
+        kw["replay"] = case.replay()
+    monkeypatch.setenv("DRJ_DRAWS", "1")
+    ahead = run_gpu(case, mode, seed=6, chain_offset=2, **kw)
+    split = run_gpu(case, mode, seed=6, chain_offset=2, iters_per_launch=5, **kw)
+    monkeypatch.setenv("DRJ_DRAWS", "0")
+    own = run_gpu(case, mode, seed=6, chain_offset=2, **kw)
+    for k in ahead:
+        if k != "t_diff":
+            assert np.array_equal(ahead[k], own[k]), k
+            assert np.array_equal(ahead[k], split[k]), k
+
+
+def test_draws_ahead_is_the_default_for_small_runs_only():
+    """One extra launch (the draw kernel) per sweep launch when the run has at most two warps per scheduler."""
+    import drjacoby_b200 as drj
+    from helpers import gpu_spec
+    case = CASES["doublewell_k2"]
+    counts = {}
+    for label, env in (("default", None), ("off", "0")):
+        if env is None:
+            os.environ.pop("DRJ_DRAWS", None)
+        else:
+            os.environ["DRJ_DRAWS"] = env
+        try:
+            s = drj.Session(drj.Model(builtin=case.model), gpu_spec(case, "philox", None, 1, 0, iters_per_launch=10))
+            s.advance(30)
+            counts[label] = s.launches()
+            s.close()
+        finally:
+            os.environ.pop("DRJ_DRAWS", None)
+    assert counts["default"][0] == counts["off"][0] == 3
+    assert counts["default"][1] - counts["off"][1] == 3, counts
 
 
 def test_chunked_launches_are_bitwise_identical():
