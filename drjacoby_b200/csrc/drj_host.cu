@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) drj_fp64_probe(double* out, int iters, do
 struct JitFuncs {
   CUmodule module = nullptr;
   CUfunction init_cu = nullptr, sweep_cu = nullptr, stream_cu = nullptr, team_init_cu = nullptr, team_sweep_cu = nullptr,
-             init_chain_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr, lanes_sweep_cu = nullptr, spec5_cu = nullptr, spec7_cu = nullptr;
+             init_chain_cu = nullptr, small_cu = nullptr, grid_init_cu = nullptr, grid_sweep_cu = nullptr, lanes_sweep_cu = nullptr, spec5_cu = nullptr, spec7_cu = nullptr;
 };
 
 struct drj_model {
@@ -383,6 +383,7 @@ struct drj_model {
   const void* init_fn = nullptr;   // built-in: __global__ function addresses
   const void* init_chain_fn = nullptr;  // initial likelihood / prior, one thread per chain
   const void* sweep_fn = nullptr;
+  const void* small_fn = nullptr;  // sweep variant for runs too small to fill the machine (drj_sweep_kernel_small)
   const void* stream_fn = nullptr; // sweep variant for data streamed through shared memory (datum-form models)
   const void* team_init_fn = nullptr;   // cluster-per-chain variants (datum-form models)
   const void* team_sweep_fn = nullptr;
@@ -419,6 +420,7 @@ struct BuiltinEntry {
   int lanes, lanes_bpp;
   const void* spec5_fn;
   const void* spec7_fn;
+  const void* small_fn;
 };
 
 #define DRJ_REG(NAME, ...)                                                               \
@@ -430,7 +432,7 @@ struct BuiltinEntry {
         DrjStreamKernel<__VA_ARGS__>::grid_init(), DrjStreamKernel<__VA_ARGS__>::grid_sweep(),         \
         DrjLanesKernel<__VA_ARGS__>::sweep(), DrjLanesKernel<__VA_ARGS__>::lanes,                      \
         DrjLanesKernel<__VA_ARGS__>::bytes_per_particle, DrjSpecKernel<__VA_ARGS__>::sweep5(),         \
-        DrjSpecKernel<__VA_ARGS__>::sweep7()                                                           \
+        DrjSpecKernel<__VA_ARGS__>::sweep7(), (const void*)drj_sweep_kernel_small<__VA_ARGS__>         \
   }
 
 static const BuiltinEntry BUILTINS[] = {
@@ -644,6 +646,9 @@ static std::string make_jit_source(const drj_model_desc* desc) {
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep(const __grid_constant__ DrjKernelArgs a) {\n"
        "  drj_sweep_body<DRJ_USER_MODEL, false, DRJ_MODE_SOLO>(a);\n"
        "}\n"
+       "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 1) drj_user_sweep_small(const __grid_constant__ DrjKernelArgs a) {\n"
+       "  drj_sweep_body<DRJ_USER_MODEL, false, DRJ_MODE_SOLO, true>(a);\n"
+       "}\n"
        "extern \"C\" __global__ void __launch_bounds__(DRJ_NT, 2) drj_user_sweep_stream(const __grid_constant__ DrjKernelArgs a) {\n"
        "  if constexpr (DRJ_USER_MODEL::DATUM_FORM) drj_sweep_body<DRJ_USER_MODEL, true, DRJ_MODE_SOLO>(a);\n"
        "}\n"
@@ -693,6 +698,7 @@ static int jit_functions(const drj_model* m, int device, const JitFuncs** out, d
   if (g_drv.ModuleGetFunction(&f.init_cu, f.module, "drj_user_init") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.sweep_cu, f.module, "drj_user_sweep") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.stream_cu, f.module, "drj_user_sweep_stream") != CUDA_SUCCESS ||
+      g_drv.ModuleGetFunction(&f.small_cu, f.module, "drj_user_sweep_small") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.team_init_cu, f.module, "drj_user_init_team") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.team_sweep_cu, f.module, "drj_user_sweep_team") != CUDA_SUCCESS ||
       g_drv.ModuleGetFunction(&f.grid_init_cu, f.module, "drj_user_init_grid") != CUDA_SUCCESS ||
@@ -816,6 +822,7 @@ extern "C" int drj_model_create(const drj_model_desc* desc, int device, drj_mode
       m->grid_init_fn = b.grid_init_fn; m->grid_sweep_fn = b.grid_sweep_fn;
       m->lanes_sweep_fn = b.lanes_sweep_fn; m->lanes = b.lanes; m->lanes_bpp = b.lanes_bpp;
       m->spec5_fn = b.spec5_fn; m->spec7_fn = b.spec7_fn; m->spec = b.spec5_fn != nullptr;
+      m->small_fn = b.small_fn;
       *out = m;
       return DRJ_OK;
     }
@@ -983,6 +990,7 @@ struct drj_session {
   bool stream_variant = false;  // data too large for shared memory: use the streaming sweep kernel
   double *draw_z = nullptr, *draw_lu = nullptr, *draw_clu = nullptr;  // draws computed ahead (DrjKernelArgs::draws)
   int* d_free_param = nullptr;  // free slot -> parameter index
+  bool small = false;           // the sweep kernel of runs too small to fill the machine (draws ahead, parallel coupling decisions)
   bool team = false;            // few chains x long data: cluster-per-chain kernels (drj_sweep_item_team)
   int team_ctas = 1;            // CTAs per cluster
   bool team_ctas_forced = false;
@@ -1162,12 +1170,13 @@ static int launch_model_kernel(drj_session* s, bool sweep, drj_error* err) {
     }
     return DRJ_OK;
   }
+  const bool small = sweep && !stream && s->small;
   if (m->jit) {
-    CUresult cr = g_drv.LaunchKernel(!sweep ? s->jf->init_cu : (stream ? s->jf->stream_cu : s->jf->sweep_cu), s->grid, 1, 1, s->nthreads, 1, 1,
+    CUresult cr = g_drv.LaunchKernel(!sweep ? s->jf->init_cu : (stream ? s->jf->stream_cu : (small ? s->jf->small_cu : s->jf->sweep_cu)), s->grid, 1, 1, s->nthreads, 1, 1,
                                      s->dyn_smem, (CUstream)s->stream, params, nullptr);
     if (cr != CUDA_SUCCESS) return cu_fail(err, "cuLaunchKernel", cr);
   } else {
-    CUDA_TRY(cudaLaunchKernel(!sweep ? m->init_fn : (stream ? m->stream_fn : m->sweep_fn), dim3(s->grid), dim3(s->nthreads),
+    CUDA_TRY(cudaLaunchKernel(!sweep ? m->init_fn : (stream ? m->stream_fn : (small ? m->small_fn : m->sweep_fn)), dim3(s->grid), dim3(s->nthreads),
                               params, s->dyn_smem, s->stream));
   }
   return DRJ_OK;
@@ -1201,11 +1210,11 @@ static int solo_configure(drj_session* s, drj_error* err) {
   if ((size_t)s->dyn_smem + 24u * (size_t)s->D + 16384u <= 48u * 1024u) return DRJ_OK;  // static + dynamic within the default limit
   const drj_model* m = s->model;
   if (m->jit) {
-    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->stream_cu, s->jf->spec5_cu, s->jf->spec7_cu})
+    for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->small_cu, s->jf->stream_cu, s->jf->spec5_cu, s->jf->spec7_cu})
       if (f && g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
         return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed (dynamic shared memory %u bytes)", s->dyn_smem);
   } else {
-    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->stream_fn, m->spec5_fn, m->spec7_fn})
+    for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->small_fn, m->stream_fn, m->spec5_fn, m->spec7_fn})
       if (f) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
   }
   return DRJ_OK;
@@ -1731,7 +1740,7 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
     // most two warps per scheduler: every update is then pure latency, and the draw is a third of it); from ~2 warps per
     // scheduler on the sweep hides that latency itself and the extra pass through HBM would only cost
     cudaDeviceProp prop3;
-    const bool solo = !s->team && !s->gridk && !s->lanes && !s->spec;
+    const bool solo = !s->team && !s->gridk && !s->lanes && !s->spec && !s->stream_variant;
     const double draw_bytes = 16.0 * ((double)s->tb + 1) * s->d_free * (double)P + 8.0 * (double)s->tb * (double)C * std::max(R - 1, 1);
     bool want = solo && s->d_free > 0 && device_props(cfg->device, &prop3) == cudaSuccess &&
                 P <= 32LL * 8 * prop3.multiProcessorCount && draw_bytes <= 1.0e9;
@@ -1748,6 +1757,12 @@ static int session_create_impl(drj_session* s, const drj_config* cfg, const drj_
       s->d_free_param = const_cast<int*>(fp);
       a.draws = 1; a.draw_z = s->draw_z; a.draw_lu = s->draw_lu; a.draw_clu = s->draw_clu;
     }
+    // (the same small runs: coupling decisions for every possible carried replica at once, drj_sampler.cuh)
+    bool par = solo && R > 1 && R <= 32 && cfg->coupling_on && device_props(cfg->device, &prop3) == cudaSuccess &&
+               P <= 32LL * 8 * prop3.multiProcessorCount;
+    if (const char* e = getenv("DRJ_COUPLE_PAR")) par = (e[0] == '1') ? (solo && R > 1 && R <= 32 && cfg->coupling_on) : (e[0] == '0' ? false : par);
+    a.couple_par = par ? 1 : 0;
+    s->small = a.draws || a.couple_par;
   }
   CUDA_TRY(upload(s, &a.block_ptr, cfg->block_ptr, D + 1));
   CUDA_TRY(upload(s, &a.block_idx, cfg->block_idx, cfg->block_ptr[D]));

@@ -65,6 +65,8 @@ struct DrjKernelArgs {
   const double* draw_z;    // [n_iter + 1][d_free][P]  (one padded row: the loads run one update ahead)
   const double* draw_lu;   // same layout
   const double* draw_clu;  // [n_iter][chains][rungs - 1]
+  int couple_par;      // one-thread-per-particle kernels, rungs <= 32, small runs: the swap decisions of a coupling pass are taken for
+                       // every possible carried replica at once, the hot-to-cold walk is integer arithmetic on those masks
   int blocks_trivial;  // a one-block model whose every free parameter lists exactly that block: no block lists are read
   unsigned lo_is_log;  // bit i: parameter i (< 32) has a lower bound of exactly 0, so its cached Jacobian logarithm
                        // log(theta_i - min_i) IS log(theta_i) (models with HINTS reuse it instead of taking the logarithm again)
@@ -1047,8 +1049,9 @@ __device__ __forceinline__ int drj_sync_or(bool warp_local, int pred) {
 // TEAM = one thread-block cluster per chain (few chains x long data, see drj_sweep_item_team): every
 // thread is a replica of rung (tid mod R) of the cluster's chain and runs the whole update redundantly;
 // `valid` = the thread holds a real particle, `active` = it is the replica that writes to HBM.
-template <class M, bool STREAM, int MODE>
+template <class M, bool STREAM, int MODE, bool SMALL = false>
 __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
+  static_assert(!SMALL || (MODE == DRJ_MODE_SOLO && !STREAM), "SMALL: one thread per particle, data resident");
   constexpr bool TEAM = MODE == DRJ_MODE_TEAM, GRID = MODE == DRJ_MODE_GRID;
   static_assert(!(STREAM && MODE != DRJ_MODE_SOLO), "TEAM / GRID replicas keep their state in registers");
   constexpr int D = M::D, B = M::NBLOCK;
@@ -1100,7 +1103,9 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
 
   // draws computed ahead (a.draws): element (it, free slot, particle) at ((it * d_free + slot) * P + p), so consecutive
   // updates of this thread are P apart; the loads run one update ahead of their use
-  const bool draws = MODE == DRJ_MODE_SOLO && a.draws != 0;
+  // (SMALL: a kernel of its own for these runs -- compiled into the kernel of the large runs, which sits at its
+  // 128-register cap, the values held across the update made it spill: n = 100 sweep -2.5 %)
+  const bool draws = SMALL && a.draws != 0;
   long long de = p;
   double z_nx = 0.0, lu_nx = 0.0;
   if (draws) { z_nx = a.draw_z[de]; lu_nx = a.draw_lu[de]; }
@@ -1250,7 +1255,65 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
     }
 
     // ================= Metropolis coupling (main.cpp:282-344) =================
-    if (do_couple) {
+    int src = r;
+    bool couple_serial = do_couple;
+    if (SMALL && do_couple && a.couple_par) {
+      // Runs too small to fill the machine (latency-bound), R <= 32.  The serial walk below costs ~26 dependent
+      // instructions per pair in ONE lane (K2, 20 rungs: 21 % of the run).  The replica carried into pair i came from
+      // some rung j <= i: thread i takes the pair's decision for EVERY such j at once (independent instructions, all
+      // lanes busy), one bit each -- the same rounded expression as the walk, main.cpp:300-308 -- and the walk itself
+      // is three integer instructions per pair on those masks, done by every thread for its own chain (no walker lane,
+      // no swap mask to publish).
+      couple_serial = false;
+      unsigned* const s_dec = reinterpret_cast<unsigned*>(s_logu);
+      s_x[tid] = s.ll;
+      drj_sync(wl);
+      if (r < R - 1) {
+        double lu;
+        if (draws) lu = clu;
+        else {
+          double u;
+          if (a.rng_mode) u = rp[3LL * a.d_free * R + r];
+          else {
+            DrjU4 w = drj_philox4x32_10(gchain_lo, (unsigned)t, (unsigned)r, 1u | (gchain_hi << 8), k0, k1);
+            u = drj_u32_to_unif(w.x);
+          }
+          lu = log(u);
+        }
+        const double ll2 = s_x[tid + 1], b1 = beta, b2 = s_beta[r + 1];
+        const double q1 = __dmul_rn(ll2, b1), q2 = __dmul_rn(ll2, b2);
+        unsigned m = 0u;
+#pragma unroll 4
+        for (int j = 0; j <= r; ++j) {
+          const double cur_ll = s_x[base + j];
+          const double t1 = __dmul_rn(cur_ll, b2), t2 = __dmul_rn(cur_ll, b1);
+          const double acceptance = (b1 == 0.0) ? __dsub_rn(t1, q2) : __dsub_rn(__dadd_rn(q1, t1), __dadd_rn(t2, q2));
+          m |= (lu < acceptance ? 1u : 0u) << j;
+        }
+        s_dec[tid] = m;
+      }
+      drj_sync(wl);
+      unsigned sw = 0u;
+      {
+        int j = 0;
+#pragma unroll 4
+        for (int i = 0; i < R - 1; ++i) {
+          const unsigned bit = (s_dec[base + i] >> j) & 1u;
+          sw |= bit << i;
+          j = bit ? j : i + 1;
+        }
+      }
+      if (valid) {
+        if (r < R - 1 && ((sw >> r) & 1u)) {
+          src = r + 1;
+          ++mc_count;
+        } else {
+          const unsigned zeros = ~sw & ((1u << r) - 1u);  // pairs below r that did not swap
+          src = zeros ? 32 - __clz(zeros) : 0;
+        }
+      }
+    }
+    if (couple_serial) {
       // parallel part: every rung publishes its loglike, the two products of the pair BELOW it that do not depend on
       // the outcome of earlier swaps (loglike2 * beta1, loglike2 * beta2: rung i+1 is untouched until pair i is
       // decided), and the pair's log u
@@ -1310,7 +1373,6 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
       drj_sync(wl);
       // parallel part: rung r receives the replica of rung r+1 if pair r swapped, else the replica that was being
       // carried up: the one from below the run of swapped pairs that ends at pair r-1
-      int src = r;
       if (valid) {
         const unsigned* sw = s_swap + (TEAM ? 0 : lc) * W;
         if (r < R - 1 && ((sw[r >> 5] >> (r & 31)) & 1u)) {
@@ -1328,6 +1390,8 @@ __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
           }
         }
       }
+    }
+    if (do_couple) {
       const int from = base + src;
       if (drj_sync_or(wl, src != r)) {
         // replica-owned state moves: theta, phi, Jacobian logs, loglike_block, loglike, logprior.
@@ -1400,6 +1464,12 @@ __global__ void __launch_bounds__(DRJ_NT) drj_init_chain_kernel(const __grid_con
 template <class M, bool STREAM>
 __global__ void __launch_bounds__(DRJ_NT, (STREAM ? 2 : DRJ_MINB)) drj_sweep_kernel(const __grid_constant__ DrjKernelArgs a) {
   drj_sweep_body<M, STREAM, DRJ_MODE_SOLO>(a);
+}
+// runs too small to fill the machine (at most two warps per scheduler): draws computed ahead, coupling decisions taken
+// for every possible carried replica at once (drj_sweep_body, SMALL); one CTA per SM is plenty, so no register cap
+template <class M>
+__global__ void __launch_bounds__(DRJ_NT, 1) drj_sweep_kernel_small(const __grid_constant__ DrjKernelArgs a) {
+  drj_sweep_body<M, false, DRJ_MODE_SOLO, true>(a);
 }
 // cluster-per-chain variants (launched with a cluster dimension of a.team_ctas; datum-form models only)
 template <class M>
