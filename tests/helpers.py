@@ -3,6 +3,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 
 POPULATION = dict(  # data/population_data.rda of the reference, decoded in SURVEY.md 8(d)
@@ -92,19 +94,20 @@ def run_gpu(case: Case, rng_mode="replay", replay=None, seed=1, chain_offset=0, 
     return drj.run_raw(m, gpu_spec(case, rng_mode, replay, seed, chain_offset, **kw))
 
 
-def rel_close(a, b, rtol=1e-10, atol=1e-12):
-    """The north_star's gate: |a - b| <= rtol |b|, plus an absolute floor of 1e-12 for values that CANCEL to (near) zero,
-    where a relative measure of the result says nothing about the arithmetic that produced it.  Why the floor is right
-    for each field it is applied to (assert_parity):
-      * log-likelihood / log-prior: a log-density is a sum of terms of order 1 (-gamma (mu^2 - 1)^2 of the double well
-        passes through 0 at mu = +-1; dnorm(.., 6, 0.1) + dnorm(.., 1, 0.1) of the test-file prior changes sign), and
-        only DIFFERENCES of log-densities enter the sampler: an absolute error of 1e-12 in log p is a relative error
-        of 1e-12 in p itself, a hundred times tighter than the gate;
-      * theta: a bounded parameter is (max e^phi + min) / (1 + e^phi); near the middle of a symmetric domain the two
-        terms cancel and the rounding error is an ulp of |min|, |max| (~1e-15 for the +-5, +-10 domains used), not of
-        the tiny result -- 1e-12 is 1e-13 of the domain width;
-      * bandwidths are strictly positive and of order 1e-3..10: the floor never applies.
-    Equal infinities and exact zeros pass."""
+# Absolute floor for the two model families whose stored values CANCEL to (near) zero, where a relative measure of the
+# result says nothing about the arithmetic that produced it; every other case is held to the pure relative gate.
+#   * double well: loglike = -gamma (mu^2 - 1)^2 passes through 0 at mu = +-1.  Only DIFFERENCES of log-densities enter
+#     the sampler: an absolute error of 1e-12 in log p is a relative error of 1e-12 in p itself, a hundred times
+#     tighter than the gate;
+#   * multilevel (symmetric +-5 domains): theta = (max e^phi + min) / (1 + e^phi) cancels near the middle of the domain,
+#     the rounding error is an ulp of |min|, |max| (~1e-15), not of the tiny result -- 1e-12 is 1e-13 of the width.
+# (Measured: with no floor anywhere, 5 of 278 GPU tests fail, all of these two families.)
+CANCELLING_ATOL = {"doublewell": 1e-12, "multilevel": 1e-12}
+
+
+def rel_close(a, b, rtol=1e-10, atol=0.0):
+    """The north_star's gate: |a - b| <= rtol |b| (atol = 0 unless the caller names a cancelling quantity, see
+    CANCELLING_ATOL).  Equal infinities and exact zeros pass."""
     a, b = np.asarray(a), np.asarray(b)
     same_inf = (np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b)))
     with np.errstate(invalid="ignore"):
@@ -115,7 +118,7 @@ def rel_close(a, b, rtol=1e-10, atol=1e-12):
     return bool(ok.all()), float(np.nanmax(rel)) if rel.size else 0.0
 
 
-def assert_parity(gpu: dict, ora, rtol=1e-10, what=""):
+def assert_parity(gpu: dict, ora, rtol=1e-10, what="", atol=0.0):
     """Replay-mode gate of BASELINE.json: states and log-likelihoods within 1e-10 relative,
     acceptance and coupling counts bit-exact."""
     for name in ["accept_burnin", "accept_sampling", "mc_accept_burnin", "mc_accept_sampling"]:
@@ -123,5 +126,5 @@ def assert_parity(gpu: dict, ora, rtol=1e-10, what=""):
         assert np.array_equal(g, o), f"{what}{name} differs: gpu {g.ravel()[:8]} oracle {o.ravel()[:8]}"
     for name in ["loglike_burnin", "logprior_burnin", "theta_burnin", "loglike_sampling", "logprior_sampling",
                  "theta_sampling", "bw_final"]:
-        ok, worst = rel_close(gpu[name], getattr(ora, name), rtol=rtol)
+        ok, worst = rel_close(gpu[name], getattr(ora, name), rtol=rtol, atol=atol)
         assert ok, f"{what}{name}: worst relative error {worst:.3e} > {rtol}"

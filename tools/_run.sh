@@ -1,3 +1,1 @@
-python tools/cfg_run.py K2 n100 n4096 2>&1 | cut -c1-150
-python tools/cfg_run.py n100 K2 2>&1 | cut -c1-150
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py tests/test_gpu_reference_suite.py -x -q 2>&1 | tail -3
+python -m pytest tests -q -m gpu 2>&1 | grep -E "^FAILED|passed|failed" | cut -c1-220 | head -40
