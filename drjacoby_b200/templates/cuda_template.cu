@@ -28,6 +28,20 @@ __device__ double logprior(const double* params, const DrjList& misc) {
 // NOTE: if your functions are not called "loglike" / "logprior", pass their names to run_mcmc().
 
 // ---------------------------------------------------------------------------------------------
+// OPTIONAL: logarithms the sampler already has (HINTS).  For every parameter with a lower bound the sampler keeps
+// log(theta_i - min_i), the Jacobian term of its reparameterisation.  Where min_i is exactly 0 (a standard deviation, a
+// rate) that IS log(theta_i), which a scale parameter's likelihood and a log-normal or gamma prior would compute again.
+// A model struct may add
+//
+//     static constexpr bool HINTS = true;
+//     __device__ static double logprior_h(const double* params, const DrjList& misc, const double* loglo, unsigned mask) {
+//       const double ls = (mask >> P_sigma & 1u) ? loglo[P_sigma] : log(params[P_sigma]);   // bit i set: loglo[i] == log(params[i])
+//       return R::dunif(params[P_mu], -10.0, 10.0, true) + R::dlnorm_l(params[P_sigma], ls, 0.0, 1.0, true);
+//     }
+//     // per-datum models also:  prepare_h(params, misc, block, k, loglo, mask)  in place of prepare()
+//
+// (logprior() / prepare() stay: they serve the initial evaluation.)  Same function of the same argument: same bits.
+// ---------------------------------------------------------------------------------------------
 // OPTIONAL: the per-datum form, for likelihoods that are a sum over many data points.
 // The functions above are evaluated by ONE GPU thread per chain x rung, which walks all the data
 // itself.  If instead you describe ONE term of the sum, the sampler stages the data once per thread

@@ -152,6 +152,46 @@ def test_nvrtc_datum_form_user_model(n):
             assert np.array_equal(a.raw[k], b.raw[k]), k
 
 
+HINTS_SRC = DATUM_SRC.replace("#define DRJ_USER_MODEL MyModel", r"""
+// the same model with the HINTS hook of cuda_template.cu: log(sigma) from the sampler's Jacobian logarithm where sigma's
+// lower bound is 0 (bit P_sigma of mask), else taken here
+struct MyHintedModel : MyModel {
+  static constexpr bool HINTS = true;
+  __device__ static bool prepare_h(const double* params, const DrjList& misc, int block, Consts& k, const double* loglo, unsigned mask) {
+    const double sd = params[P_sigma];
+    k.mean = params[P_mu];
+    k.half_inv_var = 0.5 / (sd * sd);
+    k.lognorm = 0.918938533204672741780329736406 + ((mask >> P_sigma & 1u) ? loglo[P_sigma] : log(sd));
+    return (sd > 1e-150) && (sd < 1e150) && (fabs(k.mean) < 1e150);
+  }
+  __device__ static double logprior_h(const double* params, const DrjList& misc, const double* loglo, unsigned mask) {
+    const double ls = (mask >> P_sigma & 1u) ? loglo[P_sigma] : log(params[P_sigma]);
+    return -log(20.0) + R::dlnorm_l(params[P_sigma], ls, 0.0, 1.0, true);
+  }
+};
+#define DRJ_USER_MODEL MyHintedModel
+""")
+
+
+@pytest.mark.parametrize("sigma_min", [0.0, 0.25])
+@pytest.mark.parametrize("shape", [dict(rungs=4, chains=5), dict(rungs=1, chains=2)])
+def test_nvrtc_user_model_with_hints(sigma_min, shape):
+    """The HINTS hook through NVRTC: with sigma's lower bound at 0 the model reads log(sigma) from the sampler, with any
+    other bound it takes the logarithm itself; either way bitwise the model without the hook (thread-per-particle and
+    speculative kernels)."""
+    x = np.random.default_rng(4).normal(3, 2, 100)
+    df = drj.define_params("name", "mu", "min", -10, "max", 10, "name", "sigma", "min", sigma_min, "max", np.inf)
+    kw = dict(data={"x": x}, df_params=df, loglike="loglike", logprior="logprior", burnin=20, samples=25, seed=17, silent=True,
+              as_frames=False, **shape)
+    drj.source_cuda(HINTS_SRC)
+    a = drj.run_mcmc(**kw)
+    drj.source_cuda(DATUM_SRC)
+    b = drj.run_mcmc(**kw)
+    for k in a.raw:
+        if k != "t_diff":
+            assert np.array_equal(a.raw[k], b.raw[k]), k
+
+
 def test_nvrtc_errors_are_reported():
     df = drj.define_params("name", "mu", "min", -10, "max", 10)
     drj.source_cuda("__device__ double loglike(const double* p, const DrjList& d, const DrjList& m, int b) { return undefined_symbol; }\n"

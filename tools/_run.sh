@@ -1,1 +1,2 @@
-python -m pytest tests -q -m gpu 2>&1 | grep -E "^FAILED|passed|failed" | cut -c1-220 | head -40
+python -m pytest tests/test_gpu_api.py -x -q -k "hints or datum_form" 2>&1 | tail -5
+python tools/jit_time.py 2>&1 | tail -5
