@@ -161,7 +161,8 @@ def named_configs(world, x_long=None, only=None):
         "K2": dict(model="doublewell", tmin=[-2.0, 30.0], tmax=[2.0, 30.0], what="BASELINE configs[1]: double well, 64 chains x 20 rungs, alpha = 2, "
                    "Metropolis coupling, burnin 1e3 + samples 1e4", data=[], beta=(np.linspace(0, 1, 20) ** 2.0), chains=64, burnin=1000, samples=10000,
                    full=True, scale="strong", flop=W_FIXED + 6, bound="fp64", cpu_chains=64,
-                   kernel="drj_sweep_kernel<doublewell, STREAM=0>: one thread per particle"),
+                   kernel="drj_sweep_kernel_small<doublewell>: one thread per particle, draws computed ahead by drj_draw_kernel, coupling decisions "
+                          "for every possible carried replica at once"),
         "K3": dict(model="logistic", tmin=[1.0, 1.0, 50.0], tmax=[100.0, 2.0, 200.0], what="BASELINE configs[2]: logistic growth fit to population_data "
                    "(100-step map + 20 Poisson terms per evaluation), 1024 chains x 10 rungs, burnin 1e3 + samples 1e4",
                    data=[POPULATION["pop"], POPULATION["time"]], beta=np.linspace(0, 1, 10), chains=1024, burnin=1000, samples=10000, full=True,
@@ -190,7 +191,8 @@ def named_configs(world, x_long=None, only=None):
                                       "runs its own such job: a run of this kind is a handful of chains)", data=[x_long], beta=[1.0],
                                       chains=c, burnin=11, samples=20, warm=10, ipl=10, full=False, scale="replicas", flop=FLOP_PER_DATUM * n,
                                       bound="hbm", bytes_per_sweep=8.0 * n, cpu_chains=None,
-                                      kernel="drj_sweep_kernel_grid<example>: the whole grid per run, 64 KB TMA chunks, one grid barrier per sweep")
+                                      kernel="drj_sweep_kernel_grid<example>: the whole grid per run, 64 KB TMA chunks, one grid barrier per sweep"
+                                      + (" (tile form: every thread a data slot for all chains)" if c > 1 else ""))
     if only:
         cfgs = {k: v for k, v in cfgs.items() if k in only}
     return cfgs

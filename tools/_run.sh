@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_api.py -x -q -k "hints or datum_form" 2>&1 | tail -5
-python tools/jit_time.py 2>&1 | tail -5
+S=$(date +%s); python bench.py > gpurun_out/bench_now.json 2> gpurun_out/bench_now.err; echo rc=$? elapsed=$(( $(date +%s) - S ))s
+tail -3 gpurun_out/bench_now.err | cut -c1-300
