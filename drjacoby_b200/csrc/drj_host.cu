@@ -1208,14 +1208,27 @@ static int prop_sms(const drj_session* s) {
 // plus the per-parameter tables need it (a per-datum model with many parameters)
 static int solo_configure(drj_session* s, drj_error* err) {
   if ((size_t)s->dyn_smem + 24u * (size_t)s->D + 16384u <= 48u * 1024u) return DRJ_OK;  // static + dynamic within the default limit
+  // (the attribute belongs to the function, not to the session: it only ever grows, so that a session created later
+  // with a smaller buffer does not pull it below what an earlier, still open session launches with)
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, unsigned> granted;
+  std::lock_guard<std::mutex> lock(mu);
   const drj_model* m = s->model;
+  auto need = [&](const void* f) {
+    unsigned& g = granted[std::make_pair(s->cfg.device, f)];
+    if (g >= s->dyn_smem) return 0u;
+    g = s->dyn_smem;
+    return g;
+  };
   if (m->jit) {
     for (CUfunction f : {s->jf->init_cu, s->jf->init_chain_cu, s->jf->sweep_cu, s->jf->small_cu, s->jf->stream_cu, s->jf->spec5_cu, s->jf->spec7_cu})
+      // (a module's functions die with it and their addresses may be reused: no record kept, set every time)
       if (f && g_drv.FuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->dyn_smem) != CUDA_SUCCESS)
         return set_err(err, DRJ_ERR_CUDA, "cuFuncSetAttribute failed (dynamic shared memory %u bytes)", s->dyn_smem);
   } else {
     for (const void* f : {m->init_fn, m->init_chain_fn, m->sweep_fn, m->small_fn, m->stream_fn, m->spec5_fn, m->spec7_fn})
-      if (f) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dyn_smem));
+      if (f)
+        if (const unsigned b = need(f)) CUDA_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b));
   }
   return DRJ_OK;
 }

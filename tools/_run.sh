@@ -1,2 +1,4 @@
-S=$(date +%s); python bench.py > gpurun_out/bench_now.json 2> gpurun_out/bench_now.err; echo rc=$? elapsed=$(( $(date +%s) - S ))s
-tail -3 gpurun_out/bench_now.err | cut -c1-300
+python tools/cfg_run.py n100 2>&1 | cut -c1-150
+cp drjacoby_b200/libdrjacoby_b200.so /tmp/orig.so; cp tools/libbatch.so drjacoby_b200/libdrjacoby_b200.so
+DRJ_BATCH=1 python tools/cfg_run.py n100 2>&1 | cut -c1-150
+DRJ_BATCH=1 python tools/cfg_run.py n100 2>&1 | cut -c1-150
