@@ -223,8 +223,35 @@ __device__ inline double dbinom_raw(double x, double n, double p, double q, int 
 }
 }  // namespace drj_nmath
 
+// ----------------------------------------------------------------------------- loop-invariant logarithm and reciprocal
+// A likelihood written the reference's way -- for (i) ll += R::dnorm(x[i], mu, sigma, true) -- asks for log(sigma) and a
+// division by sigma once per TERM.  Both are inline code with a rare-case branch inside, which the compiler can
+// neither hoist out of the user's loop nor overlap between terms: measured on the README example's model, 100 data
+// points, 24.1 us per update, of which 14 us the repeated logarithm and 6.5 us the division.  As calls of functions
+// that are not inlined and have no side effects they ARE loop-invariant code to the compiler (hoisted out of the
+// user's loop; removed where the result is unused, e.g. a literal sigma of 1).  R::dnorm then forms
+// z = (x - mu) * (1 / sigma): the product differs from R's quotient by at most an ulp of z (1e-16 relative, six orders
+// inside the parity gate; -DDRJ_DNORM_EXACT_DIV keeps the quotient).
+__device__ __noinline__ double drj_log_invariant(double x) { return log(x); }
+__device__ __noinline__ double drj_rcp_invariant(double x) { return 1.0 / x; }
+
 namespace R {
 __device__ __forceinline__ double dnorm(double x, double mu, double sigma, int lg) {
+  {
+    const double logsig = drj_log_invariant(sigma);
+    const double inv = drj_rcp_invariant(sigma);
+    // (everything formed before the test, so that neither call sinks into a conditional block and stays in the loop)
+#ifdef DRJ_DNORM_EXACT_DIV
+    const double zm = (x - mu) / sigma;
+#else
+    const double zm = (x - mu) * inv;
+#endif
+    const double val = -(DRJ_LN_SQRT_2PI + 0.5 * zm * zm + logsig);
+    // With sigma a normal number whose reciprocal is normal too, this expression IS R's answer for every x and mu: |z|
+    // beyond 2 sqrt(DBL_MAX) or infinite gives z^2 = Inf and the value -Inf (R_D__0); a NaN anywhere, or Inf - Inf,
+    // gives NaN.  So the test depends on sigma alone: loop-invariant in the user's loop, no data-dependent branch per term.
+    if (lg && sigma != 1.0 && sigma >= 2.2250738585072014e-308 && sigma <= 1e300) return val;
+  }
   // Regular arguments first, behind ONE fused test (a NaN anywhere fails a comparison); R's edge cases after it.  The
   // regular path is the last line of R's dnorm4 with the same operations: the d = 50 multilevel model evaluates 55 of
   // these per update, and the chain of seven separate tests and branches was 2/3 of each term's instructions (round-2 ncu).
