@@ -1,1 +1,1 @@
-python tools/generic_probe.py 2>&1 | cut -c1-200
+python -m pytest tests/test_gpu_nmath.py -x -q 2>&1 | tail -12
