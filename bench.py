@@ -160,7 +160,7 @@ def named_configs(world, x_long=None, only=None):
                    kernel="drj_sweep_kernel_spec<example, 7>: one CTA per chain, seven updates in flight (127 speculative proposals per pass)"),
         "K2": dict(model="doublewell", tmin=[-2.0, 30.0], tmax=[2.0, 30.0], what="BASELINE configs[1]: double well, 64 chains x 20 rungs, alpha = 2, "
                    "Metropolis coupling, burnin 1e3 + samples 1e4", data=[], beta=(np.linspace(0, 1, 20) ** 2.0), chains=64, burnin=1000, samples=10000,
-                   full=True, scale="strong", flop=W_FIXED + 6, bound="fp64", cpu_chains=64,
+                   full=True, scale="strong", flop=W_FIXED + 6, bound="latency", cpu_chains=64,
                    kernel="drj_sweep_kernel_small<doublewell>: one thread per particle, draws computed ahead by drj_draw_kernel, coupling decisions "
                           "for every possible carried replica at once"),
         "K3": dict(model="logistic", tmin=[1.0, 1.0, 50.0], tmax=[100.0, 2.0, 200.0], what="BASELINE configs[2]: logistic growth fit to population_data "
@@ -256,7 +256,8 @@ def run_named_config(drj, name, c, rank, world, device, fp64_peak, hbm_peak, red
                            "nominal_frac": tf / FP64_NOMINAL_TFLOPS, "per": "GPU", "algorithmic_flop_per_update": c["flop"],
                            "note": "algorithmic FP64 work per parameter update from SURVEY 8(d) (4 n sweep flop + ~400 fixed-part instructions; "
                                    "model-specific terms for K2-K4) x updates/s per GPU; peak = FP64 FMA probe of this run, nominal = 148 SM x 64 FMA/clk x 1965 MHz"
-                                   + ("; a single dependent chain: latency-bound, not a throughput shape" if c["bound"] == "latency" else "")}
+                                   + ("; too few particles to fill the machine (every thread one dependent chain): latency-bound, not a throughput shape"
+                                      if c["bound"] == "latency" else "")}
     return out
 
 
