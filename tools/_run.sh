@@ -1,6 +1,3 @@
-export PATH=/usr/local/cuda/bin:$PATH
-python -m pytest tests -q -m gpu 2>&1 | tail -3
-python bench.py --impl reference > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err; echo ref rc=$?
-python bench.py > gpurun_out/bench_n1_final.json 2> gpurun_out/bench_n1_final.err; echo n1 rc=$?
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_final.csv python bench.py > gpurun_out/ncu_bench.log 2>&1; echo ncu rc=$?
-wc -l gpurun_out/launches_final.csv
+python -m pytest tests/test_gpu_multi.py tests/test_gpu_multi_abi.py -q 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/bench_n2_final.json 2> gpurun_out/bench_n2_final.err; echo n2 rc=$?
+tail -c 600 gpurun_out/bench_n2_final.json
