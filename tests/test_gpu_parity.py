@@ -46,6 +46,10 @@ CASES = {
                              burnin=6, samples=6, save_hot_draws=True),
     "example_rungs256": Case("example", [-10, 0], [10, np.inf], data=[normal_data(8)], beta=beta_ladder(256), chains=2,
                              burnin=5, samples=5),
+    # sigma on a bounded domain with lower bound 0 (logit transform): the HINTS hook reads log(sigma) from the Jacobian
+    # logarithm log(sigma - 0) of that transform too; and with a lower bound that is not 0 the model takes its own
+    "example_sigma_logit": Case("example", [-10, 0], [10, 10], data=[normal_data(60)], beta=beta_ladder(3), chains=4),
+    "example_sigma_min_half": Case("example", [-10, 0.5], [10, np.inf], data=[normal_data(60)], beta=beta_ladder(2), chains=3),
     "example_one_chain": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100)], chains=1, burnin=300, samples=300),
     # BASELINE configs[0] at its full length: 1 chain, 1 rung, burnin 1e3 + samples 1e4, n = 100 (22,000 dependent updates)
     "k1_full_length": Case("example", [-10, 0], [10, np.inf], data=[normal_data(100, 1)], chains=1, burnin=1000, samples=10000),
@@ -156,10 +160,11 @@ def test_draws_computed_ahead_are_the_same_draws(name, mode, monkeypatch):
     if mode == "replay":
         kw["replay"] = case.replay()
     monkeypatch.setenv("DRJ_DRAWS", "1")
-    ahead = run_gpu(case, mode, seed=6, chain_offset=2, **kw)
-    split = run_gpu(case, mode, seed=6, chain_offset=2, iters_per_launch=5, **kw)
+    off = (1 << 33) + 2  # (a global chain id beyond 32 bits: both halves go into the Philox counter)
+    ahead = run_gpu(case, mode, seed=6, chain_offset=off, **kw)
+    split = run_gpu(case, mode, seed=6, chain_offset=off, iters_per_launch=5, **kw)
     monkeypatch.setenv("DRJ_DRAWS", "0")
-    own = run_gpu(case, mode, seed=6, chain_offset=2, **kw)
+    own = run_gpu(case, mode, seed=6, chain_offset=off, **kw)
     for k in ahead:
         if k != "t_diff":
             assert np.array_equal(ahead[k], own[k]), k
