@@ -158,6 +158,11 @@ def named_configs(world, x_long=None, only=None):
                    beta=[1.0], chains=1, burnin=1000, samples=10000, full=True, scale="replicas", flop=FLOP_PER_DATUM * 100 + W_FIXED,
                    bound="latency", cpu_chains=1,
                    kernel="drj_sweep_kernel_spec<example, 7>: one CTA per chain, seven updates in flight (127 speculative proposals per pass)"),
+        "default5": dict(ex, what="run_mcmc's default shape (R/main.R:213-216: chains = 5, rungs = 1) on the K1 model and data, burnin 1e3 + "
+                         "samples 1e4; the reference runs the five chains one after the other on one core unless a cluster is passed",
+                         data=[x100], beta=[1.0], chains=5, burnin=1000, samples=10000, full=True, scale="replicas",
+                         flop=FLOP_PER_DATUM * 100 + W_FIXED, bound="latency", cpu_chains=5, cpu_threads=1,
+                         kernel="drj_sweep_kernel_spec<example, 7>: one CTA per chain, the five chains side by side"),
         "K2": dict(model="doublewell", tmin=[-2.0, 30.0], tmax=[2.0, 30.0], what="BASELINE configs[1]: double well, 64 chains x 20 rungs, alpha = 2, "
                    "Metropolis coupling, burnin 1e3 + samples 1e4", data=[], beta=(np.linspace(0, 1, 20) ** 2.0), chains=64, burnin=1000, samples=10000,
                    full=True, scale="strong", flop=W_FIXED + 6, bound="latency", cpu_chains=64,
@@ -275,7 +280,7 @@ def cpu_named_config(name, c, cores, budget_chains=None):
     else:
         chains, burnin, samples, same = cores, c["burnin"], min(c["samples"], 100 if name == "K4" else 500), False
     init = default_init(c["chains"], 4242, tmin, tmax)[:chains]
-    threads = min(cores, chains)
+    threads = c.get("cpu_threads") or min(cores, chains)
     t0 = time.perf_counter()
     po.run(c["model"], c["data"], [], tmin, tmax, init, burnin=burnin, samples=samples, beta_raised=np.asarray(c["beta"], float),
            blocks=c.get("blocks"), rng_mode="philox", seed=1, n_threads=threads)
@@ -577,7 +582,7 @@ def run_reference(args):
     steps_done = len(vals)
     configs_out = {}
     if not args.no_sweeps:
-        only = {"K1", "K2", "K3"} & set(args.configs.split(",")) if args.configs else {"K1", "K2", "K3"}
+        only = {"K1", "default5", "K2", "K3"} & set(args.configs.split(",")) if args.configs else {"K1", "default5", "K2", "K3"}
         for name, c in named_configs(1, None, only).items():
             configs_out[name] = dict(cpu_named_config(name, c, cores), workload=c["what"])
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,

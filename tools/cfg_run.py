@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import bench
 import drjacoby_b200 as drj
 
-names = sys.argv[1:] or ["K1", "K2", "K3", "K4", "n100", "n4096"]
+names = sys.argv[1:] or ["K1", "default5", "K2", "K3", "K4", "n100", "n4096"]
 x_long = bench.synth_data(100_000_000) if any(n.startswith("hbm") for n in names) else None
 fp64 = drj.fp64_peak_tflops(0)
 for name, c in bench.named_configs(1, x_long, set(names)).items():
