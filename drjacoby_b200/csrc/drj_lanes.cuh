@@ -139,6 +139,7 @@ struct DrjLanesShared {
 
 template <class M>
 __device__ __forceinline__ void drj_lanes_sweep_body(const DrjKernelArgs& a) {
+  DrjCtaInit<M>::run(a);
   typedef DrjLanesTraits<M> TR;
   constexpr int L = TR::L, D = TR::D, B = TR::B, RBS = TR::RBS, RGS = TR::RGS;
   constexpr bool BATCH = TR::BATCH;

@@ -243,6 +243,39 @@ __device__ __forceinline__ double drj_logistic_step(double x, double r, double c
 struct DrjModelLogistic {
   static constexpr int D = 3, NBLOCK = 1;
   static constexpr bool DATUM_FORM = false;
+  // The Poisson terms' data-only parts, once per thread block (DrjCtaInit): of R::dpois(pop_j, x, log) the Stirling error of
+  // pop_j (three to five FP64 divisions) and log(2 pi pop_j) do not depend on the parameters.  [0, 32): stirlerr,
+  // [32, 64): the logarithm, [64, 96): the rounded count, or -1 where the count is not a regular one (or there are
+  // more than 32 observations) and R::dpois itself is called.
+  static constexpr bool CTA_INIT = true;
+  static constexpr int MAXOBS = 32;
+  __device__ static __forceinline__ double* pois_consts() {
+    __shared__ double s_pc[3 * MAXOBS];
+    return s_pc;
+  }
+  __device__ static __forceinline__ void cta_init(const DrjList& data, const DrjList&) {
+    double* const pc = pois_consts();
+    const double* pop = data.item(0);
+    const int n = (int)data.len(0);
+    for (int j = threadIdx.x; j < MAXOBS; j += blockDim.x) {
+      double st = 0.0, lf = 0.0, xr = -1.0;
+      if (j < n && n <= MAXOBS) {
+        const double x = pop[j];
+        if (!isnan(x) && !drj_nmath::nonint(x) && x >= 0.0 && isfinite(x)) {
+          xr = nearbyint(x);
+          st = drj_nmath::stirlerr(xr);
+          lf = log(DRJ_2PI * xr);
+        }
+      }
+      pc[j] = st; pc[MAXOBS + j] = lf; pc[2 * MAXOBS + j] = xr;
+    }
+  }
+  __device__ static __forceinline__ double pois_term(const double* pop, int j, double lambda) {
+    const double* const pc = pois_consts();
+    const double xr = j < MAXOBS ? pc[2 * MAXOBS + j] : -1.0;
+    if (xr >= 0.0) return R::dpois_pre(xr, lambda, pc[j], pc[MAXOBS + j]);
+    return R::dpois(pop[j], lambda, 1);
+  }
   __device__ static double loglike(const double* th, const DrjList& data, const DrjList&, int) {
     const double N_0 = th[0], r = th[1], N_max = th[2];
     const double K = N_max * r / (r - 1.0);
@@ -259,7 +292,7 @@ struct DrjModelLogistic {
       const int tj = (int)time[j];
       if (tj < step) { x = N_0; step = 1; }
       for (; step < tj; ++step) x = drj_logistic_step(x, r, c);
-      ret += R::dpois(pop[j], x, 1);
+      ret += pois_term(pop, j, x);
     }
     return ret;
   }
@@ -303,14 +336,14 @@ struct DrjModelLogistic {
 #pragma unroll
       for (int q = 0; q < MAXQ; ++q) {
         const int j = lane + q * LANES;
-        if (j < n) ret += R::dpois(pop[j], xs[q], 1);
+        if (j < n) ret += pois_term(pop, j, xs[q]);
       }
     } else {  // times that go backwards, or a long series: every lane walks to each of its own observations
       for (int j = lane; j < n; j += LANES) {
         const int tj = (int)time[j];
         x = N_0;
         for (step = 1; step < tj; ++step) x = drj_logistic_step(x, r, c);
-        ret += R::dpois(pop[j], x, 1);
+        ret += pois_term(pop, j, x);
       }
     }
     return ret;

@@ -810,6 +810,21 @@ struct DrjHints<M, decltype((void)M::HINTS)> {
   }
 };
 
+// Optional model hook (CTA_INIT): `static constexpr bool CTA_INIT = true` + `cta_init(data, misc)`, called by every
+// thread of every thread block before the block evaluates the model for the first time (followed by a block barrier):
+// the place to put quantities that depend on the data alone into shared memory the model owns.
+template <class M, class = void>
+struct DrjCtaInit {
+  __device__ static __forceinline__ void run(const DrjKernelArgs&) {}
+};
+template <class M>
+struct DrjCtaInit<M, decltype((void)M::CTA_INIT)> {
+  __device__ static __forceinline__ void run(const DrjKernelArgs& a) {
+    M::cta_init(a.data, a.misc);
+    __syncthreads();
+  }
+};
+
 template <class M, int MODE>
 __device__ __forceinline__ double drj_eval_loglike(DrjTiles<M, true>& T, const DrjKernelArgs& a,
                                                    const double* theta, int block, int own, const double* loglo = nullptr) {
@@ -902,6 +917,7 @@ template <class M>
 __device__ __forceinline__ void drj_init_chain_body(const DrjKernelArgs& a) {
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UB = DRJ_UNROLL_N(B);
+  DrjCtaInit<M>::run(a);
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = c < a.chains;
   const long long cc = active ? c : 0;  // inactive threads shadow chain 0 (uniform control flow)
@@ -936,6 +952,7 @@ __device__ __forceinline__ void drj_init_chain_body(const DrjKernelArgs& a) {
 // GRID: every CTA holds a replica of every particle (thread tid < P = particle tid); CTA 0's write to HBM.
 template <class M, int MODE>
 __device__ __forceinline__ void drj_init_body(const DrjKernelArgs& a) {
+  DrjCtaInit<M>::run(a);
   constexpr bool TEAM = MODE == DRJ_MODE_TEAM, GRID = MODE == DRJ_MODE_GRID;
   constexpr int D = M::D, B = M::NBLOCK;
   constexpr int UD = DRJ_UNROLL_N(D), UB = DRJ_UNROLL_N(B);
@@ -1052,6 +1069,7 @@ __device__ __forceinline__ int drj_sync_or(bool warp_local, int pred) {
 template <class M, bool STREAM, int MODE, bool SMALL = false>
 __device__ __forceinline__ void drj_sweep_body(const DrjKernelArgs& a) {
   static_assert(!SMALL || (MODE == DRJ_MODE_SOLO && !STREAM), "SMALL: one thread per particle, data resident");
+  DrjCtaInit<M>::run(a);
   constexpr bool TEAM = MODE == DRJ_MODE_TEAM, GRID = MODE == DRJ_MODE_GRID;
   static_assert(!(STREAM && MODE != DRJ_MODE_SOLO), "TEAM / GRID replicas keep their state in registers");
   constexpr int D = M::D, B = M::NBLOCK;

@@ -58,6 +58,7 @@ __device__ __forceinline__ int drj_picki(const int (&v)[D], int i) {
 
 template <class M, int H>
 __device__ __forceinline__ void drj_spec_sweep_body(const DrjKernelArgs& a) {
+  DrjCtaInit<M>::run(a);
   constexpr int D = M::D, NN = 1 << H, NW = NN / 32;  // threads = nodes 1 .. NN-1 (thread 0 doubles node 1), warps
   static_assert(M::NBLOCK == 1 && D <= DRJ_SPEC_MAXD, "SPEC kernels: one block, d <= 4");
   static_assert(H >= 5 && H <= 8, "SPEC kernels: 5 to 8 updates in flight");
