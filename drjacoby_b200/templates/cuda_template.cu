@@ -42,6 +42,17 @@ __device__ double logprior(const double* params, const DrjList& misc) {
 //
 // (logprior() / prepare() stay: they serve the initial evaluation.)  Same function of the same argument: same bits.
 // ---------------------------------------------------------------------------------------------
+// OPTIONAL: quantities that depend on the data alone (CTA_INIT).  A model struct may add
+//
+//     static constexpr bool CTA_INIT = true;
+//     __device__ static double* my_consts() { __shared__ double c[64]; return c; }       // shared memory the model owns
+//     __device__ static void cta_init(const DrjList& data, const DrjList& misc) {        // every thread of every block, once
+//       for (int j = threadIdx.x; j < 64 && j < data.len(DATA_y); j += blockDim.x) my_consts()[j] = lgamma(data.item(DATA_y)[j] + 1.0);
+//     }
+//
+// and read my_consts() in loglike(): cta_init runs before the block's first evaluation of the model and is followed by a
+// block barrier.  (The built-in logistic-growth model keeps the Stirling error and log(2 pi y) of its Poisson counts there.)
+// ---------------------------------------------------------------------------------------------
 // OPTIONAL: the per-datum form, for likelihoods that are a sum over many data points.
 // The functions above are evaluated by ONE GPU thread per chain x rung, which walks all the data
 // itself.  If instead you describe ONE term of the sum, the sampler stages the data once per thread

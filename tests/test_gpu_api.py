@@ -192,6 +192,61 @@ def test_nvrtc_user_model_with_hints(sigma_min, shape):
             assert np.array_equal(a.raw[k], b.raw[k]), k
 
 
+POIS_SRC = r"""
+// a Poisson regression y_j ~ Pois(exp(a + b t_j)) as a model struct; with -DUSE_INIT the lgamma(y_j + 1) terms come from
+// the CTA_INIT hook of cuda_template.cu instead of being recomputed at every evaluation
+struct PoisModel {
+  static constexpr int D = DRJ_D, NBLOCK = DRJ_NBLOCK;
+  static constexpr bool DATUM_FORM = false;
+#ifdef USE_INIT
+  static constexpr bool CTA_INIT = true;
+  __device__ static double* consts() { __shared__ double c[64]; return c; }
+  __device__ static void cta_init(const DrjList& data, const DrjList& misc) {
+    for (int j = threadIdx.x; j < 64 && j < data.len(DATA_y); j += blockDim.x) consts()[j] = lgamma(data.item(DATA_y)[j] + 1.0);
+  }
+#endif
+  __device__ static double loglike(const double* params, const DrjList& data, const DrjList& misc, int block) {
+    double ll = 0.0;
+    for (int j = 0; j < (int)data.len(DATA_y); ++j) {
+      const double eta = params[P_a] + params[P_b] * data.item(DATA_t)[j];
+#ifdef USE_INIT
+      const double lg = consts()[j];
+#else
+      const double lg = lgamma(data.item(DATA_y)[j] + 1.0);
+#endif
+      ll += data.item(DATA_y)[j] * eta - exp(eta) - lg;
+    }
+    return ll;
+  }
+  __device__ static double logprior(const double* params, const DrjList& misc) {
+    return R::dnorm(params[P_a], 0.0, 10.0, true) + R::dnorm(params[P_b], 0.0, 10.0, true);
+  }
+};
+#define DRJ_USER_MODEL PoisModel
+"""
+
+
+@pytest.mark.parametrize("shape", [dict(rungs=5, chains=7), dict(rungs=1, chains=3), dict(rungs=2, chains=400)])
+def test_nvrtc_user_model_with_cta_init(shape):
+    """The CTA_INIT hook through NVRTC on every kernel family a generic model can take (small-run, speculative, the
+    general one-thread-per-particle kernel): the data-only terms formed once per block give the bits of the model that
+    recomputes them."""
+    rng = np.random.default_rng(8)
+    t = np.linspace(0.0, 2.0, 40)
+    y = rng.poisson(np.exp(0.5 + 0.8 * t)).astype(float)
+    df = drj.define_params("name", "a", "min", -5, "max", 5, "name", "b", "min", -5, "max", 5)
+    kw = dict(data={"y": y, "t": t}, df_params=df, loglike="loglike", logprior="logprior", burnin=20, samples=25, seed=3, silent=True,
+              as_frames=False, **shape)
+    drj.source_cuda("#define USE_INIT 1\n" + POIS_SRC)
+    a = drj.run_mcmc(**kw)
+    drj.source_cuda(POIS_SRC)
+    b = drj.run_mcmc(**kw)
+    assert np.isfinite(a.raw["loglike_sampling"]).all()
+    for k in a.raw:
+        if k != "t_diff":
+            assert np.array_equal(a.raw[k], b.raw[k]), k
+
+
 def test_nvrtc_errors_are_reported():
     df = drj.define_params("name", "mu", "min", -10, "max", 10)
     drj.source_cuda("__device__ double loglike(const double* p, const DrjList& d, const DrjList& m, int b) { return undefined_symbol; }\n"

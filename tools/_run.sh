@@ -1,2 +1,1 @@
-python tools/cfg_run.py K3 2>&1 | cut -c1-140
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_lanes.py tests/test_gpu_fullsize.py tests/test_gpu_api.py -x -q 2>&1 | tail -3
+python -m pytest tests/test_gpu_api.py -x -q -k "cta_init" 2>&1 | tail -8
