@@ -1,3 +1,3 @@
-python -m pytest tests -q -m gpu 2>&1 | tail -3
-python bench.py > gpurun_out/bench_n1_final.json 2> gpurun_out/bench_n1_final.err; echo n1 rc=$?
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 > gpurun_out/bench_n2_final.json 2> gpurun_out/bench_n2_final.err; echo n2 rc=$?
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err; echo ref rc=$?
+tail -c 300 gpurun_out/bench_ref_n2.json
