@@ -172,6 +172,32 @@ __device__ inline double stirlerr(double n) {
   return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
 }
 
+// a / (2 j + 1), correctly rounded, without the division: for the divisors the series of bd0 uses, the correctly rounded
+// reciprocal y is a constant, and with it q = RN(a y), r = a - b q (exact, one FMA), q' = RN(q + r y) IS RN(a / b)
+// (Markstein's quotient step; checked against exact rational arithmetic, tools/markstein_check.py, and on the device
+// against the division itself, tests/test_gpu_nmath.py).  CUDA's own division does the same after refining its
+// reciprocal at run time: ~15 instructions and a branch against 3.  Outside a wide regular range of a (no underflow of the
+// residual, no overflow) and for j >= 32 the division itself.
+__device__ const double DRJ_RCP_ODD[32] = {
+    0x1.0000000000000p+0, 0x1.5555555555555p-2, 0x1.999999999999ap-3, 0x1.2492492492492p-3,
+    0x1.c71c71c71c71cp-4, 0x1.745d1745d1746p-4, 0x1.3b13b13b13b14p-4, 0x1.1111111111111p-4,
+    0x1.e1e1e1e1e1e1ep-5, 0x1.af286bca1af28p-5, 0x1.8618618618618p-5, 0x1.642c8590b2164p-5,
+    0x1.47ae147ae147bp-5, 0x1.2f684bda12f68p-5, 0x1.1a7b9611a7b96p-5, 0x1.0842108421084p-5,
+    0x1.f07c1f07c1f08p-6, 0x1.d41d41d41d41dp-6, 0x1.bacf914c1bad0p-6, 0x1.a41a41a41a41ap-6,
+    0x1.8f9c18f9c18fap-6, 0x1.7d05f417d05f4p-6, 0x1.6c16c16c16c17p-6, 0x1.5c9882b931057p-6,
+    0x1.4e5e0a72f0539p-6, 0x1.4141414141414p-6, 0x1.3521cfb2b78c1p-6, 0x1.29e4129e4129ep-6,
+    0x1.1f7047dc11f70p-6, 0x1.15b1e5f75270dp-6, 0x1.0c9714fbcda3bp-6, 0x1.0410410410410p-6};
+__device__ __forceinline__ double drj_div_odd(double a, int j) {
+  const double b = (double)((j << 1) + 1);
+  if (j < 32 && fabs(a) > 1e-280 && fabs(a) < 1e280) {
+    const double y = DRJ_RCP_ODD[j];
+    const double q = a * y;
+    const double r = fma(-b, q, a);
+    return fma(r, y, q);
+  }
+  return a / b;
+}
+
 // x log(x/np) + np - x, stable near x == np
 __device__ inline double bd0(double x, double np) {
   if (!isfinite(x) || !isfinite(np) || np == 0.0) return DRJ_NAN;
@@ -183,7 +209,7 @@ __device__ inline double bd0(double x, double np) {
     v = v * v;
     for (int j = 1; j < 1000; j++) {
       ej *= v;
-      double s1 = s + ej / ((j << 1) + 1);
+      double s1 = s + drj_div_odd(ej, j);
       if (s1 == s) return s1;
       s = s1;
     }

@@ -48,3 +48,34 @@ def test_device_dnorm_follows_r(oracle):
             assert g == (2e300 if want > 0 else -2e300), (args[k], g, want)
         else:
             assert abs(g - want) <= 4e-16 * max(1.0, abs(want)) + 1e-15 * abs(0.5 * ((a - b) / c) ** 2), (args[k], g, want)
+
+
+DIV_SRC = r'''
+// drj_div_odd(a, j) (the division-free quotient of nmath's bd0 series) against the division itself, bit for bit:
+// 32 divisors x 200,000 pseudo-random dividends (mantissas from an LCG, exponents -270 .. 270, both signs) per evaluation
+__device__ double loglike(const double* params, const DrjList& data, const DrjList& misc, int block) {
+  unsigned long long state = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)(params[0] * 1e6);
+  int bad = 0;
+  for (int it = 0; it < 200000; ++it) {
+    state = state * 6364136223846793005ULL + 1442695040888963407ULL;
+    const unsigned long long mant = (state >> 12) | 0x0010000000000000ULL;
+    const int e = (int)((state >> 3) % 541ULL) - 270;
+    double a = ldexp((double)mant, e - 52);
+    if (state & 4ULL) a = -a;
+    for (int j = 0; j < 32; ++j) {
+      const double q1 = drj_nmath::drj_div_odd(a, j), q2 = a / (double)(2 * j + 1);
+      bad += (__double_as_longlong(q1) != __double_as_longlong(q2)) ? 1 : 0;
+    }
+  }
+  return -(double)bad;
+}
+__device__ double logprior(const double* params, const DrjList& misc) { return 0.0; }
+'''
+
+
+def test_division_free_quotient_is_the_quotient():
+    import drjacoby_b200 as drj
+    case = Case("jit", [0.0], [1.0], chains=8, burnin=2, samples=1)
+    out = run_gpu(case, "philox", seed=1, model=drj.Model(source=DIV_SRC))
+    # 8 chains x (initial evaluation + 2 proposals) x 6.4e6 comparisons, every one equal
+    assert np.all(out["loglike_burnin"] == 0.0) and np.all(out["loglike_sampling"] == 0.0)

@@ -1,3 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 > gpurun_out/bench_n2_final.json 2> gpurun_out/bench_n2_final.err; echo n2 rc=$?
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err; echo ref rc=$?
-tail -c 300 gpurun_out/bench_ref_n2.json
+python -m pytest tests/test_gpu_nmath.py -x -q 2>&1 | tail -4
+python tools/cfg_run.py K3 2>&1 | cut -c1-140
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_lanes.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
