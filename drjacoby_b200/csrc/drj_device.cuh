@@ -187,14 +187,15 @@ __device__ const double DRJ_RCP_ODD[32] = {
     0x1.8f9c18f9c18fap-6, 0x1.7d05f417d05f4p-6, 0x1.6c16c16c16c17p-6, 0x1.5c9882b931057p-6,
     0x1.4e5e0a72f0539p-6, 0x1.4141414141414p-6, 0x1.3521cfb2b78c1p-6, 0x1.29e4129e4129ep-6,
     0x1.1f7047dc11f70p-6, 0x1.15b1e5f75270dp-6, 0x1.0c9714fbcda3bp-6, 0x1.0410410410410p-6};
+__device__ __forceinline__ double drj_quot_odd(double a, double b, int j) {  // b = 2 j + 1, j < 32, a in the regular range
+  const double y = DRJ_RCP_ODD[j];
+  const double q = a * y;
+  const double r = fma(-b, q, a);
+  return fma(r, y, q);
+}
 __device__ __forceinline__ double drj_div_odd(double a, int j) {
   const double b = (double)((j << 1) + 1);
-  if (j < 32 && fabs(a) > 1e-280 && fabs(a) < 1e280) {
-    const double y = DRJ_RCP_ODD[j];
-    const double q = a * y;
-    const double r = fma(-b, q, a);
-    return fma(r, y, q);
-  }
+  if (j < 32 && fabs(a) > 1e-280 && fabs(a) < 1e280) return drj_quot_odd(a, b, j);
   return a / b;
 }
 
@@ -207,9 +208,14 @@ __device__ inline double bd0(double x, double np) {
     if (fabs(s) < DRJ_DBL_MIN) return s;
     double ej = 2 * x * v;
     v = v * v;
+    // (the terms only shrink, and the loop ends when a term falls below half an ulp of s: with s and the first term in
+    // a regular range every dividend of the first 31 terms is, and the test is made once, not per term)
+    const bool regular = fabs(s) > 1e-250 && fabs(ej) < 1e250;
+    double bj = 1.0;
     for (int j = 1; j < 1000; j++) {
       ej *= v;
-      double s1 = s + drj_div_odd(ej, j);
+      bj += 2.0;  // 2 j + 1
+      double s1 = s + ((regular && j < 32) ? drj_quot_odd(ej, bj, j) : ej / bj);
       if (s1 == s) return s1;
       s = s1;
     }

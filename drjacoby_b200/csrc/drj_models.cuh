@@ -328,8 +328,9 @@ struct DrjModelLogistic {
       const int tj = (int)time[j];
       if (tj < step) { monotone = false; break; }
       for (; step < tj; ++step) x = drj_logistic_step(x, r, c);
-#pragma unroll
-      for (int q = 0; q < MAXQ; ++q) xs[q] = (j == lane + q * LANES) ? x : xs[q];
+      // (one store with a run-time index by the lane that owns observation j: the select over all MAXQ slots that kept xs
+      // in registers was 13 % of the K3 run's instructions, round-2 ncu; the array now lives in local memory, L1-resident)
+      if ((j & (LANES - 1)) == lane) xs[j / LANES] = x;
     }
     double ret = 0.0;
     if (monotone) {
