@@ -327,6 +327,7 @@ struct DrjModelLogistic {
     for (int j = 0; j < n && monotone; ++j) {  // uniform over the lanes
       const int tj = (int)time[j];
       if (tj < step) { monotone = false; break; }
+#pragma unroll 4
       for (; step < tj; ++step) x = drj_logistic_step(x, r, c);
       // (one store with a run-time index by the lane that owns observation j: the select over all MAXQ slots that kept xs
       // in registers was 13 % of the K3 run's instructions, round-2 ncu; the array now lives in local memory, L1-resident)
