@@ -1,2 +1,3 @@
-python tools/cfg_run.py K3 2>&1 | cut -c1-140
-python -m pytest tests/test_gpu_nmath.py tests/test_gpu_parity.py tests/test_gpu_lanes.py tests/test_gpu_fullsize.py -x -q 2>&1 | tail -3
+python -m pytest tests -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --configs K3,K1 --hbm-n 0 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo rc=$?
